@@ -1,0 +1,121 @@
+/*
+ * rendertoy_b200.h -- C ABI of librendertoy_b200.so (hand-written sm_100a CUDA behind the reference's
+ * `rendering` Python package).  Plain pointers and sizes only; no torch / C++ types cross this line.
+ *
+ * The reference (lleonart1984/rendertoy) has no FFI of its own: its device boundary is pyopencl kernel
+ * launches issued from rendering/_raster.py and rendering/_core.py.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds to rendering/_raster.py / _raycaster.py to switch over.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative rt_status; rt_last_error() gives the text
+ *     (thread-local, valid until the next failing call on that thread);
+ *   - every `d_` pointer is DEVICE memory owned by the caller (the Python side passes
+ *     torch.Tensor.data_ptr()); the library allocates nothing except texture objects and the NCCL
+ *     communicator, which have explicit create/destroy calls;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued
+ *     asynchronously on it and no entry point synchronises unless its comment says so;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with RT_ERR_CUDA.
+ */
+#ifndef RENDERTOY_B200_H
+#define RENDERTOY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1, /* bad argument */
+    RT_ERR_CUDA = -2,    /* CUDA runtime error (text in rt_last_error) */
+    RT_ERR_NCCL = -3,
+    RT_ERR_UNSUPPORTED = -4
+} rt_status;
+
+/* Built-in shader pairs (vertex + fragment), recognised by the Python side from the tutorial sources. */
+#define RT_SHADER_LESSON08 8 /* tutorials/lesson08_rasterization.py:36-62: Lambert max(0.2, N.l), colour = C      */
+#define RT_SHADER_LESSON09 9 /* tutorials/lesson09_texture_mapping.py:67-95: L = 0.2+max(0,N.l), tex(P.xy*2) * L */
+
+#define RT_NO_PRIMITIVE 0xFFFFFFFFu /* low word of a key no primitive has won in the current draw */
+
+int rt_abi_version(void);
+const char *rt_last_error(void);
+/* SM count, L2 bytes, compute capability of the current device. */
+int rt_device_info(int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor);
+
+/* ---- mesh upload -------------------------------------------------------------------------------
+ * AoS MeshVertex[n] (80 B: P@0 N@16 C@32 T@48 B@64; rendering/_modeling.py:22-28, filled by
+ * rendering/_loaders.py:16-38) -> SoA float4 position and normal arrays, the layout every kernel
+ * below reads with 128-bit loads.  Replaces the per-draw 80 B/vertex reads of VertexProcess
+ * (rendering/_raster.py:63-73). */
+int rt_mesh_upload_soa(const void *d_mesh_vertices, int64_t n_vertices, void *d_pos4, void *d_nrm4, void *stream);
+
+/* ---- render-target / depth clears  (rendering/_core.py:376-388 clear()) --------------------------
+ * The depth buffer lives in the high word of a W*H array of 64-bit keys (depth_bits << 32 | primitive);
+ * clearing writes (depth_bits << 32 | RT_NO_PRIMITIVE). */
+int rt_raster_clear_depth(void *d_key, int64_t n_pixels, uint32_t depth_bits, void *stream);
+/* BGRA8 target (CL_BGRA / CL_UNORM_INT8, rendering/_core.py:340): fill with rgba converted sat+rte. */
+int rt_raster_clear_color(void *d_bgra, int64_t n_pixels, const float rgba[4], void *stream);
+/* Raster.get_depth_buffer() view (rendering/_raster.py:388-389): gather / scatter the uint32 depth words. */
+int rt_raster_read_depth(const void *d_key, int64_t n_pixels, void *d_depth_u32, void *stream);
+int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32, void *stream);
+
+/* ---- Raster.draw_triangles  (rendering/_raster.py:416-437) -----------------------------------------
+ * One call = VertexProcess + TriangleAssembly(+near clip) + Dehomogenize + TriangleRaster + DepthTest
+ * + FragmentProcess of the reference (kernels at _raster.py:63-73, 152-205, 118-133, 227-327, 80-93,
+ * 95-112), executed as two kernels: (1) fused vertex/clip/setup/coverage with a 64-bit atomicMin on the
+ * packed key, (2) resolve: re-interpolate the winning primitive per pixel, run the fragment shader once,
+ * write BGRA8, re-arm the key's low word.  No host synchronisation, no intermediate fragment stream.
+ *
+ *   d_pos4, d_nrm4   SoA vertex arrays from rt_mesh_upload_soa
+ *   d_indices        int32 triangle indices or NULL for a triangle soup (_raster.py:156-158)
+ *   vs_globals       48 floats: Transforms{World, View, Proj} row-major (lesson08:19-23), HOST memory,
+ *                    passed by value like the reference passes struct arguments (_core.py:270-274)
+ *   tex_handle       0, or a handle from rt_texture_create (lesson09 Materials.DiffuseMap)
+ *   d_key            W*H 64-bit keys (persistent across draws of a frame, like the depth buffer)
+ *   d_records        scratch, >= rt_raster_record_bytes(shader, n_triangles) bytes
+ *   d_bgra           W*H*4 bytes, the render target
+ */
+int64_t rt_raster_record_bytes(int shader, int64_t n_triangles);
+int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles,
+                             int shader, const float *vs_globals, uint64_t tex_handle, int width, int height,
+                             void *d_key, void *d_records, void *d_bgra, void *stream);
+
+/* ---- textures  (rendering/_core.py:551-578 MemoryPool / create_texture2D, :94-96 sample2D) ---------
+ * Point-sampled float4 CUDA texture object over caller-owned linear device memory (row 0 first).
+ * d_texels must be 512-byte aligned. */
+int rt_texture_create(const void *d_texels, int width, int height, uint64_t *out_handle);
+int rt_texture_destroy(uint64_t handle);
+
+/* ---- ray casting  (rendering/_raycaster.py:8-36: BVH_AABB, BVH_Triangle, Raycaster) ----------------
+ * The reference ships only the skeleton (ray_cast is `pass`); semantics are defined in
+ * oracle/raycast_oracle.c.  LBVH: 30-bit Morton codes of triangle centroids -> LSD radix sort ->
+ * Karras hierarchy -> bottom-up AABB refit; traversal is a persistent-thread stack walk. */
+int64_t rt_bvh_node_bytes(int64_t n_triangles);    /* bytes of d_nodes  */
+int64_t rt_bvh_tri_bytes(int64_t n_triangles);     /* bytes of d_tris   */
+int64_t rt_bvh_scratch_bytes(int64_t n_triangles); /* bytes of d_scratch (build only) */
+/* Raycaster._build_ads (rendering/_raycaster.py:30-33). d_tri_ids (uint32[n]) receives the original
+ * triangle id of each sorted leaf. */
+int rt_bvh_build(const void *d_pos4, const int32_t *d_indices, int64_t n_triangles, void *d_nodes, void *d_tris,
+                 void *d_tri_ids, void *d_scratch, void *stream);
+/* Raycaster.ray_cast (rendering/_raycaster.py:35-36): rays = n x {float3 origin, float3 dir} (32 B),
+ * hits = n x {float t, uint32 triangle, float u, float v} (16 B); miss: t = +inf, triangle = 0xFFFFFFFF. */
+int rt_raycast_rays(const void *d_nodes, const void *d_tris, const void *d_tri_ids, int64_t n_triangles,
+                    const void *d_rays, int64_t n_rays, void *d_hits, void *stream);
+/* Fused primary-ray generation + closest hit + Lambert/texture shade for the pixel rect
+ * [x0,x0+w) x [y0,y0+h) of a width x height frame.  camera = {origin, U, V, W} (12 floats, model space,
+ * HOST memory): dir = (U*sx + V*sy) + W.  Outputs are rect-local, row-major: d_hits (16 B/pixel, may be
+ * NULL), d_bgra (4 B/pixel, pitch `bgra_pitch_px` pixels so a rank can write straight into a frame). */
+int rt_raycast_primary(const void *d_nodes, const void *d_tris, const void *d_tri_ids, int64_t n_triangles,
+                       const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
+                       int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
+                       int64_t bgra_pitch_px, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENDERTOY_B200_H */

@@ -1,0 +1,564 @@
+// rt_raster.cu -- Raster.draw_triangles for sm_100a (replaces rendering/_raster.py:416-437 and the seven
+// OpenCL kernels it drives).  Two kernels per draw, no host round trip, no fragment stream:
+//
+//   raster_kernel   one thread per input triangle: vertex shader x3, near clip into <=2 primitives,
+//                   dehomogenize, bbox + edge setup (all bit-identical to the reference arithmetic), one
+//                   64 B/96 B setup record per primitive; then the block's primitives are staged in shared
+//                   memory and their bbox cells are spread evenly over all 256 threads (prefix sum + search),
+//                   each cell doing the reference's coverage test and a 64-bit atomicMin of
+//                   (depth_bits << 32 | primitive id) into the key buffer.
+//   resolve_kernel  one thread per pixel: decode the winning key, re-evaluate that primitive at the pixel
+//                   from its record, perspective-correct attributes, fragment shader once, BGRA8 store,
+//                   re-arm the key's low word for the next draw.
+//
+// Bound: HBM (vertices in, keys/colour out) with an L2-atomic sub-bound; no dense contraction, so no
+// tensor cores.
+#include "rt_common.cuh"
+
+namespace {
+
+constexpr int RB = 256; // threads per raster block = triangles per block iteration
+
+struct VO { // vertex-shader output: clip-space position + up to 3 attribute floats
+    float x, y, z, w, a0, a1, a2;
+};
+
+struct DrawArgs {
+    const float4 *pos, *nrm;
+    const int *idx;
+    long long n_tris;
+    float g[48]; // World, View, Proj
+    int width, height;
+    float half_w, half_h;
+    unsigned long long *key;
+    float4 *rec;
+};
+
+// ---- reference arithmetic, restated -----------------------------------------------------------
+
+// _core.py:86-88 mul(float4, float4x4): r_j = dot(v, column j)
+__device__ __forceinline__ float4 mul4(float4 v, const float *m)
+{
+    float4 r;
+    r.x = ((v.x * m[0] + v.y * m[4]) + v.z * m[8]) + v.w * m[12];
+    r.y = ((v.x * m[1] + v.y * m[5]) + v.z * m[9]) + v.w * m[13];
+    r.z = ((v.x * m[2] + v.y * m[6]) + v.z * m[10]) + v.w * m[14];
+    r.w = ((v.x * m[3] + v.y * m[7]) + v.z * m[11]) + v.w * m[15];
+    return r;
+}
+
+// lesson08:41-54 (SHADER 8) / lesson09:72-86 (SHADER 9)
+template <int SHADER>
+__device__ __forceinline__ VO vertex_shader(float4 P, float4 N, const float *g)
+{
+    const float n = RT_INV_SQRT3;
+    float dt = (N.x * n + N.y * n) + N.z * n;
+    float4 H = make_float4(P.x, P.y, P.z, 1.0f);
+    H = mul4(H, g);
+    H = mul4(H, g + 16);
+    H = mul4(H, g + 32);
+    VO o;
+    o.x = H.x; o.y = H.y; o.z = H.z; o.w = H.w;
+    if (SHADER == RT_SHADER_LESSON08) {
+        o.a0 = fmaxf(0.2f, dt); o.a1 = 0.0f; o.a2 = 0.0f;
+    } else {
+        o.a0 = 0.2f + fmaxf(0.0f, dt); o.a1 = P.x * 2.0f; o.a2 = P.y * 2.0f;
+    }
+    return o;
+}
+
+// _raster.py:25-40 interpolate2: v0*(1-alpha) + v1*alpha on every field
+template <int SHADER>
+__device__ __forceinline__ VO lerp_vo(const VO &a, const VO &b, float alpha)
+{
+    const float om = 1.0f - alpha;
+    VO o;
+    o.x = a.x * om + b.x * alpha; o.y = a.y * om + b.y * alpha;
+    o.z = a.z * om + b.z * alpha; o.w = a.w * om + b.w * alpha;
+    o.a0 = a.a0 * om + b.a0 * alpha;
+    if (SHADER == RT_SHADER_LESSON09) { o.a1 = a.a1 * om + b.a1 * alpha; o.a2 = a.a2 * om + b.a2 * alpha; }
+    else { o.a1 = 0.0f; o.a2 = 0.0f; }
+    return o;
+}
+
+// _raster.py:126-129 Dehomogenize
+__device__ __forceinline__ void dehomogenize(VO &p, float half_w, float half_h)
+{
+    p.x = p.x / p.w; p.y = p.y / p.w; p.z = p.z / p.w;
+    p.y = p.y * -1.0f;
+    p.x = p.x + 1.0f; p.y = p.y + 1.0f;
+    p.x = p.x * half_w; p.y = p.y * half_h;
+}
+
+struct Edges { // _raster.py:274-292
+    float a1, b1, c1, a2, b2, c2, a3, b3, c3;
+    unsigned tle; // bit0: v1v2, bit1: v2v3, bit2: v3v1 is a top/left edge
+};
+
+__device__ __forceinline__ Edges edge_setup(float h1x, float h1y, float h2x, float h2y, float h3x, float h3y)
+{
+    Edges e;
+    e.a1 = h2y - h1y; e.b1 = h1x - h2x; e.c1 = h1x * (h1y - h2y) - h1y * (h1x - h2x);
+    e.a2 = h3y - h2y; e.b2 = h2x - h3x; e.c2 = h2x * (h2y - h3y) - h2y * (h2x - h3x);
+    e.a3 = h1y - h3y; e.b3 = h3x - h1x; e.c3 = h3x * (h3y - h1y) - h3y * (h3x - h1x);
+    unsigned t12 = ((h1y == h2y && h2x <= h1x) || h1y < h2y) ? 1u : 0u;
+    unsigned t23 = ((h2y == h3y && h3x <= h2x) || h2y < h3y) ? 2u : 0u;
+    unsigned t31 = ((h3y == h1y && h1x <= h3x) || h3y < h1y) ? 4u : 0u;
+    e.tle = t12 | t23 | t31;
+    return e;
+}
+
+struct BBox { int startx, starty, nx, ny; }; // nx*ny == 0 when nothing is to be rasterized
+
+// _raster.py:237-241 + the `pixel_count < 64*64` gate of :294
+__device__ __forceinline__ BBox bbox_setup(float x1, float y1, float x2, float y2, float x3, float y3, int W, int H)
+{
+    int minx = (int)fminf(x1, fminf(x2, x3)), miny = (int)fminf(y1, fminf(y2, y3));
+    int maxx = (int)fmaxf(x1, fmaxf(x2, x3)), maxy = (int)fmaxf(y1, fmaxf(y2, y3));
+    long long sx = max(0, minx), sy = max(0, miny);
+    long long ex = min((long long)(W - 1), 1ll + maxx), ey = min((long long)(H - 1), 1ll + maxy);
+    long long nx = ex - sx + 1, ny = ey - sy + 1;
+    BBox b;
+    b.startx = (int)sx; b.starty = (int)sy;
+    if (nx <= 0 || ny <= 0 || nx * ny >= 64 * 64) { b.nx = 0; b.ny = 0; }
+    else { b.nx = (int)nx; b.ny = (int)ny; }
+    return b;
+}
+
+struct Cell { // _raster.py:298-311 for one (col,row)
+    float al1, al2, al3;
+    bool inside;
+};
+
+__device__ __forceinline__ Cell cell_eval(const Edges &e, int col, int row)
+{
+    const float eps = 1e-8f; // (float)0.00000001, _raster.py:290-292
+    float px = (float)col + 0.5f, py = (float)row + 0.5f;
+    float d1 = e.a1 * px + e.b1 * py + e.c1;
+    float d2 = e.a2 * px + e.b2 * py + e.c2;
+    float d3 = e.a3 * px + e.b3 * py + e.c3;
+    float s = d1 + d2 + d3;
+    Cell c;
+    c.al3 = d1 / s; c.al1 = d2 / s; c.al2 = d3 / s;
+    float comp3 = (e.tle & 1u) ? 0.0f : eps, comp1 = (e.tle & 2u) ? 0.0f : eps, comp2 = (e.tle & 4u) ? 0.0f : eps;
+    c.inside = c.al1 >= comp1 && c.al2 >= comp2 && c.al3 >= comp3;
+    return c;
+}
+
+__device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, float w2, float w3)
+{
+    return f1 * w1 + f2 * w2 + f3 * w3;
+}
+
+// ---- kernel 1: vertex + clip + setup + coverage + depth atomics ---------------------------------
+
+struct Slot { // per-primitive coverage data staged in shared memory (21 words: odd stride, conflict-free)
+    float h1x, h1y, h1z, h2x, h2y, h2z, h3x, h3y, h3z;
+    float a1, b1, c1, a2, b2, c2, a3, b3, c3;
+    int sxy;       // startx | starty << 16
+    int nx_tle;    // nx | tle << 16
+    unsigned prim; // 2*t + k
+};
+
+template <int SHADER> struct RecLayout { static constexpr int F4 = SHADER == RT_SHADER_LESSON08 ? 4 : 6; };
+
+template <int SHADER>
+__device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3, unsigned prim, Slot &s)
+{
+    dehomogenize(p1, a.half_w, a.half_h);
+    dehomogenize(p2, a.half_w, a.half_h);
+    dehomogenize(p3, a.half_w, a.half_h);
+    if (p1.z < 0) return 0; // _raster.py:236
+    BBox bb = bbox_setup(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, a.width, a.height);
+    if (bb.nx == 0) return 0;
+    float e1x = p2.x - p1.x, e1y = p2.y - p1.y, e2x = p3.x - p1.x, e2y = p3.y - p1.y;
+    if (!((e1x * e2y - e1y * e2x) <= 0)) { VO t = p2; p2 = p3; p3 = t; } // :259-266
+    Edges e = edge_setup(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+
+    float4 *r = a.rec + (size_t)prim * RecLayout<SHADER>::F4;
+    r[0] = make_float4(p1.x, p1.y, p1.z, p1.w);
+    r[1] = make_float4(p2.x, p2.y, p2.z, p2.w);
+    r[2] = make_float4(p3.x, p3.y, p3.z, p3.w);
+    r[3] = make_float4(p1.a0, p2.a0, p3.a0, 0.0f);
+    if (SHADER == RT_SHADER_LESSON09) {
+        r[4] = make_float4(p1.a1, p1.a2, p2.a1, p2.a2);
+        r[5] = make_float4(p3.a1, p3.a2, 0.0f, 0.0f);
+    }
+    s.h1x = p1.x; s.h1y = p1.y; s.h1z = p1.z;
+    s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
+    s.h3x = p3.x; s.h3y = p3.y; s.h3z = p3.z;
+    s.a1 = e.a1; s.b1 = e.b1; s.c1 = e.c1;
+    s.a2 = e.a2; s.b2 = e.b2; s.c2 = e.c2;
+    s.a3 = e.a3; s.b3 = e.b3; s.c3 = e.c3;
+    s.sxy = bb.startx | (bb.starty << 16);
+    s.nx_tle = bb.nx | ((int)e.tle << 16);
+    s.prim = prim;
+    return bb.nx * bb.ny;
+}
+
+// _raster.py:152-205 TriangleAssembly: clip code, lerped vertices, first/second output triangle
+template <int SHADER>
+__device__ __forceinline__ int assemble(const DrawArgs &a, long long t, VO (&q)[2][3])
+{
+    long long i0 = 3 * t, i1 = 3 * t + 1, i2 = 3 * t + 2;
+    if (a.idx) { i0 = a.idx[i0]; i1 = a.idx[i1]; i2 = a.idx[i2]; }
+    VO v0 = vertex_shader<SHADER>(__ldg(a.pos + i0), __ldg(a.nrm + i0), a.g);
+    VO v1 = vertex_shader<SHADER>(__ldg(a.pos + i1), __ldg(a.nrm + i1), a.g);
+    VO v2 = vertex_shader<SHADER>(__ldg(a.pos + i2), __ldg(a.nrm + i2), a.g);
+    int clip = (v0.z < 0 ? 1 : 0) | (v1.z < 0 ? 2 : 0) | (v2.z < 0 ? 4 : 0);
+    if (clip == 0) { q[0][0] = v0; q[0][1] = v1; q[0][2] = v2; return 1; }
+    if (clip == 7) return 0;
+    VO v01 = lerp_vo<SHADER>(v0, v1, -v0.z / (v1.z - v0.z));
+    VO v12 = lerp_vo<SHADER>(v1, v2, -v1.z / (v2.z - v1.z));
+    VO v20 = lerp_vo<SHADER>(v2, v0, -v2.z / (v0.z - v2.z));
+    switch (clip) {
+    case 1: q[0][0] = v01; q[0][1] = v1;  q[0][2] = v2;  q[1][0] = v01; q[1][1] = v2;  q[1][2] = v20; return 2;
+    case 2: q[0][0] = v0;  q[0][1] = v01; q[0][2] = v12; q[1][0] = v0;  q[1][1] = v12; q[1][2] = v2;  return 2;
+    case 3: q[0][0] = v12; q[0][1] = v2;  q[0][2] = v20; return 1;
+    case 4: q[0][0] = v0;  q[0][1] = v1;  q[0][2] = v12; q[1][0] = v0;  q[1][1] = v12; q[1][2] = v20; return 2;
+    case 5: q[0][0] = v01; q[0][1] = v1;  q[0][2] = v12; return 1;
+    default: q[0][0] = v0; q[0][1] = v01; q[0][2] = v20; return 1; // 6
+    }
+}
+
+template <int SHADER>
+__global__ void __launch_bounds__(RB) raster_kernel(const DrawArgs a)
+{
+    __shared__ Slot slots[RB];
+    __shared__ int cell_off[RB + 1];
+    __shared__ int warp_tot[RB / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int W = a.width, H = a.height;
+
+    for (long long base = (long long)blockIdx.x * RB; base < a.n_tris; base += (long long)gridDim.x * RB) {
+        const long long t = base + tid;
+        VO q[2][3];
+        int nprim = 0;
+        if (t < a.n_tris) nprim = assemble<SHADER>(a, t, q);
+
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1) {
+                if (!__syncthreads_or(nprim > 1)) break; // second output triangles are rare (near-plane only)
+            }
+            int ncells = 0;
+            if (k < nprim) ncells = setup_prim<SHADER>(a, q[k][0], q[k][1], q[k][2], (unsigned)(2 * t + k), slots[tid]);
+
+            // block-wide exclusive scan of ncells -> cell_off
+            int incl = ncells;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) warp_tot[wid] = incl;
+            __syncthreads();
+            int wbase = 0;
+#pragma unroll
+            for (int w = 0; w < RB / 32; ++w) wbase += (w < wid) ? warp_tot[w] : 0;
+            cell_off[tid] = wbase + incl - ncells;
+            if (tid == RB - 1) cell_off[RB] = wbase + incl;
+            __syncthreads();
+            const int total = cell_off[RB];
+
+            for (int c = tid; c < total; c += RB) {
+                int lo = 0, hi = RB; // largest p with cell_off[p] <= c
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int mid = (lo + hi) >> 1;
+                    if (cell_off[mid] <= c) lo = mid; else hi = mid;
+                }
+                const Slot &s = slots[lo];
+                const int local = c - cell_off[lo];
+                const int nx = s.nx_tle & 0xffff;
+                const int r = (int)(((float)local + 0.5f) * __frcp_rn((float)nx)); // exact for local,nx < 4096
+                const int col = (s.sxy & 0xffff) + (local - r * nx), row = (s.sxy >> 16) + r;
+                Edges e;
+                e.a1 = s.a1; e.b1 = s.b1; e.c1 = s.c1; e.a2 = s.a2; e.b2 = s.b2; e.c2 = s.c2;
+                e.a3 = s.a3; e.b3 = s.b3; e.c3 = s.c3; e.tle = (unsigned)(s.nx_tle >> 16);
+                Cell cl = cell_eval(e, col, row);
+                if (!cl.inside) continue;
+                float hx = blend3(s.h1x, s.h2x, s.h3x, cl.al1, cl.al2, cl.al3);
+                float hy = blend3(s.h1y, s.h2y, s.h3y, cl.al1, cl.al2, cl.al3);
+                float hz = blend3(s.h1z, s.h2z, s.h3z, cl.al1, cl.al2, cl.al3);
+                if (hz < 0) continue; // DepthTest, _raster.py:85
+                int ix = (int)hx, iy = (int)hy; // the INTERPOLATED position picks the pixel (:88-89)
+                if (ix < 0 || ix >= W || iy < 0 || iy >= H) continue;
+                unsigned long long k64 = ((unsigned long long)__float_as_uint(hz) << 32) | s.prim;
+                atomicMin(a.key + (size_t)iy * W + ix, k64);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- kernel 2: resolve + fragment shader ----------------------------------------------------------
+
+struct ResolveArgs {
+    unsigned long long *key;
+    const float4 *rec;
+    uint32_t *bgra;
+    int width, height;
+    cudaTextureObject_t tex;
+    int tex_w, tex_h;
+};
+
+struct PrimRec { float4 h1, h2, h3; };
+
+// Slow path (practically never taken): the winning fragment was produced by a loop cell other than the
+// pixel itself, because (int) of the interpolated position landed elsewhere.  Search the bbox in row-major
+// order for the first cell of this primitive that maps to (x,y) with these depth bits.
+__device__ __noinline__ bool find_source_cell(const PrimRec &p, const Edges &e, int x, int y, uint32_t zbits, int W, int H,
+                                               int *col_out, int *row_out)
+{
+    BBox bb = bbox_setup(p.h1.x, p.h1.y, p.h2.x, p.h2.y, p.h3.x, p.h3.y, W, H);
+    for (int r = 0; r < bb.ny; ++r)
+        for (int c = 0; c < bb.nx; ++c) {
+            int col = bb.startx + c, row = bb.starty + r;
+            Cell cl = cell_eval(e, col, row);
+            if (!cl.inside) continue;
+            float hx = blend3(p.h1.x, p.h2.x, p.h3.x, cl.al1, cl.al2, cl.al3);
+            float hy = blend3(p.h1.y, p.h2.y, p.h3.y, cl.al1, cl.al2, cl.al3);
+            float hz = blend3(p.h1.z, p.h2.z, p.h3.z, cl.al1, cl.al2, cl.al3);
+            if (hz < 0 || (int)hx != x || (int)hy != y || __float_as_uint(hz) != zbits) continue;
+            *col_out = col; *row_out = row;
+            return true;
+        }
+    return false;
+}
+
+template <int SHADER>
+__global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs a)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.width || y >= a.height) return;
+    const size_t p = (size_t)y * a.width + x;
+    const unsigned long long k64 = a.key[p];
+    const unsigned prim = (unsigned)k64;
+    if (prim == RT_NO_PRIMITIVE) return;
+    const uint32_t zbits = (uint32_t)(k64 >> 32);
+
+    const float4 *r = a.rec + (size_t)prim * RecLayout<SHADER>::F4;
+    PrimRec pr;
+    pr.h1 = __ldg(r); pr.h2 = __ldg(r + 1); pr.h3 = __ldg(r + 2);
+    const float4 at = __ldg(r + 3);
+    Edges e = edge_setup(pr.h1.x, pr.h1.y, pr.h2.x, pr.h2.y, pr.h3.x, pr.h3.y);
+
+    int col = x, row = y;
+    Cell cl = cell_eval(e, col, row);
+    {
+        float hx = blend3(pr.h1.x, pr.h2.x, pr.h3.x, cl.al1, cl.al2, cl.al3);
+        float hy = blend3(pr.h1.y, pr.h2.y, pr.h3.y, cl.al1, cl.al2, cl.al3);
+        float hz = blend3(pr.h1.z, pr.h2.z, pr.h3.z, cl.al1, cl.al2, cl.al3);
+        if (!(cl.inside && (int)hx == x && (int)hy == y && __float_as_uint(hz) == zbits)) {
+            if (find_source_cell(pr, e, x, y, zbits, a.width, a.height, &col, &row)) cl = cell_eval(e, col, row);
+        }
+    }
+    // _raster.py:313-318 perspective-correct weights, interpolate3 with (beta2, beta3)
+    float q1 = cl.al1 / pr.h1.w, q2 = cl.al2 / pr.h2.w, q3 = cl.al3 / pr.h3.w;
+    float qs = q1 + q2 + q3;
+    float beta2 = q2 / qs, beta3 = q3 / qs;
+    float w1 = 1.0f - beta2 - beta3;
+    float4 color;
+    if (SHADER == RT_SHADER_LESSON08) { // lesson08:58-62
+        float c = blend3(at.x, at.y, at.z, w1, beta2, beta3);
+        color = make_float4(c, c, c, 1.0f);
+    } else {                            // lesson09:90-95
+        const float4 uv12 = __ldg(r + 4), uv3 = __ldg(r + 5);
+        float L = blend3(at.x, at.y, at.z, w1, beta2, beta3);
+        float cx = blend3(uv12.x, uv12.z, uv3.x, w1, beta2, beta3);
+        float cy = blend3(uv12.y, uv12.w, uv3.y, w1, beta2, beta3);
+        float4 tx = rt_sample2d(a.tex, a.tex_w, a.tex_h, cx, cy);
+        color = make_float4(tx.x * L, tx.y * L, tx.z * L, 1.0f);
+    }
+    const float z = __uint_as_float(zbits);
+    if (!(z <= 0)) a.bgra[p] = rt_pack_bgra(color.x, color.y, color.z, color.w); // FragmentProcess, :102
+    a.key[p] = k64 | 0xFFFFFFFFull; // re-arm: later draws win depth ties, as in the reference's draw order
+}
+
+// ---- clears and depth views -----------------------------------------------------------------------
+
+__global__ void fill_u64_kernel(ulonglong2 *dst, long long n2, unsigned long long v, unsigned long long *tail, int ntail)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const ulonglong2 vv = make_ulonglong2(v, v);
+    for (; i < n2; i += stride) dst[i] = vv;
+    if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = v;
+}
+
+__global__ void fill_u32_kernel(uint4 *dst, long long n4, uint32_t v, uint32_t *tail, int ntail)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint4 vv = make_uint4(v, v, v, v);
+    for (; i < n4; i += stride) dst[i] = vv;
+    if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = v;
+}
+
+__global__ void read_depth_kernel(const unsigned long long *key, long long n, uint32_t *out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)(key[i] >> 32);
+}
+
+__global__ void write_depth_kernel(unsigned long long *key, long long n, const uint32_t *in)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = ((unsigned long long)in[i] << 32) | 0xFFFFFFFFull;
+}
+
+int fill_grid(long long n_vec)
+{
+    long long blocks = (n_vec + 255) / 256;
+    long long cap = (long long)rt_sm_count() * 8;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+struct rt_texture {
+    cudaTextureObject_t obj;
+    int w, h;
+};
+
+template <int SHADER>
+int launch_draw(const DrawArgs &da, const ResolveArgs &ra, cudaStream_t st)
+{
+    if (da.n_tris > 0) {
+        int per_sm = 0;
+        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel<SHADER>, RB, 0));
+        long long want = (da.n_tris + RB - 1) / RB, cap = (long long)rt_sm_count() * (per_sm > 0 ? per_sm : 1);
+        raster_kernel<SHADER><<<(int)(want < cap ? want : cap), RB, 0, st>>>(da);
+        RT_CUDA(cudaGetLastError());
+    }
+    dim3 grid((ra.width + 31) / 32, (ra.height + 7) / 8), block(32, 8);
+    resolve_kernel<SHADER><<<grid, block, 0, st>>>(ra);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_raster_clear_depth(void *d_key, int64_t n_pixels, uint32_t depth_bits, void *stream)
+{
+    RT_REQUIRE(d_key && n_pixels >= 0, "key buffer");
+    RT_REQUIRE(((uintptr_t)d_key & 15) == 0, "key buffer must be 16-byte aligned");
+    if (n_pixels == 0) return RT_OK;
+    unsigned long long v = ((unsigned long long)depth_bits << 32) | 0xFFFFFFFFull;
+    long long n2 = n_pixels / 2;
+    fill_u64_kernel<<<fill_grid(n2), 256, 0, (cudaStream_t)stream>>>((ulonglong2 *)d_key, n2, v,
+                                                                    (unsigned long long *)d_key + 2 * n2, (int)(n_pixels - 2 * n2));
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_raster_clear_color(void *d_bgra, int64_t n_pixels, const float rgba[4], void *stream)
+{
+    RT_REQUIRE(d_bgra && rgba && n_pixels >= 0, "colour buffer");
+    RT_REQUIRE(((uintptr_t)d_bgra & 15) == 0, "colour buffer must be 16-byte aligned");
+    if (n_pixels == 0) return RT_OK;
+    // host-side replica of rt_pack_bgra (sat, x255, round to nearest even)
+    uint32_t px = 0;
+    const int order[4] = {2, 1, 0, 3};
+    for (int i = 0; i < 4; ++i) {
+        float v = rgba[order[i]] * 255.0f;
+        if (!(v > 0.0f)) v = 0.0f;
+        if (v > 255.0f) v = 255.0f;
+        px |= (uint32_t)__builtin_nearbyintf(v) << (8 * i);
+    }
+    long long n4 = n_pixels / 4;
+    fill_u32_kernel<<<fill_grid(n4), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_bgra, n4, px, (uint32_t *)d_bgra + 4 * n4,
+                                                                    (int)(n_pixels - 4 * n4));
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_raster_read_depth(const void *d_key, int64_t n_pixels, void *d_depth_u32, void *stream)
+{
+    RT_REQUIRE(d_key && d_depth_u32 && n_pixels >= 0, "buffers");
+    if (n_pixels == 0) return RT_OK;
+    read_depth_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)d_key, n_pixels,
+                                                                                           (uint32_t *)d_depth_u32);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32, void *stream)
+{
+    RT_REQUIRE(d_key && d_depth_u32 && n_pixels >= 0, "buffers");
+    if (n_pixels == 0) return RT_OK;
+    write_depth_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>((unsigned long long *)d_key, n_pixels,
+                                                                                            (const uint32_t *)d_depth_u32);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+int64_t rt_raster_record_bytes(int shader, int64_t n_triangles)
+{
+    int f4 = shader == RT_SHADER_LESSON08 ? 4 : 6;
+    return 2 * n_triangles * f4 * 16; // up to two primitives per input triangle
+}
+
+int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles, int shader,
+                             const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_records,
+                             void *d_bgra, void *stream)
+{
+    RT_REQUIRE(n_triangles >= 0 && n_triangles < (1ll << 31), "triangle count (primitive ids are 32-bit: 2*t+k)");
+    RT_REQUIRE(n_triangles == 0 || (d_pos4 && d_nrm4 && d_records), "vertex arrays / record scratch");
+    RT_REQUIRE(vs_globals && d_key && d_bgra, "globals / targets");
+    RT_REQUIRE(width > 0 && height > 0 && width <= 32768 && height <= 32768, "viewport");
+    RT_REQUIRE(shader == RT_SHADER_LESSON08 || shader == RT_SHADER_LESSON09, "shader id");
+    DrawArgs da;
+    da.pos = (const float4 *)d_pos4; da.nrm = (const float4 *)d_nrm4; da.idx = d_indices; da.n_tris = n_triangles;
+    for (int i = 0; i < 48; ++i) da.g[i] = vs_globals[i];
+    da.width = width; da.height = height;
+    da.half_w = (float)width * 0.5f; da.half_h = (float)height * 0.5f; // viewport_dim * 0.5f, _raster.py:129
+    da.key = (unsigned long long *)d_key; da.rec = (float4 *)d_records;
+    ResolveArgs ra;
+    ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
+    ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
+    if (shader == RT_SHADER_LESSON09) {
+        RT_REQUIRE(tex_handle != 0, "lesson09 shader needs a texture handle");
+        const rt_texture *t = (const rt_texture *)(uintptr_t)tex_handle;
+        ra.tex = t->obj; ra.tex_w = t->w; ra.tex_h = t->h;
+        return launch_draw<RT_SHADER_LESSON09>(da, ra, (cudaStream_t)stream);
+    }
+    return launch_draw<RT_SHADER_LESSON08>(da, ra, (cudaStream_t)stream);
+}
+
+int rt_texture_create(const void *d_texels, int width, int height, uint64_t *out_handle)
+{
+    RT_REQUIRE(d_texels && out_handle && width > 0 && height > 0, "texture arguments");
+    RT_REQUIRE(((uintptr_t)d_texels & 511) == 0, "texel pointer must be 512-byte aligned");
+    RT_REQUIRE((long long)width * height <= (1ll << 27), "linear texture limited to 2^27 texels");
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<void *>(d_texels);
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+    rd.res.linear.sizeInBytes = (size_t)width * height * 16;
+    cudaTextureDesc td = {};
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    rt_texture *t = new rt_texture{0, width, height};
+    cudaError_t e = cudaCreateTextureObject(&t->obj, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        delete t;
+        rt_set_error("cudaCreateTextureObject: %s", cudaGetErrorString(e));
+        return RT_ERR_CUDA;
+    }
+    *out_handle = (uint64_t)(uintptr_t)t;
+    return RT_OK;
+}
+
+int rt_texture_destroy(uint64_t handle)
+{
+    if (!handle) return RT_OK;
+    rt_texture *t = (rt_texture *)(uintptr_t)handle;
+    cudaDestroyTextureObject(t->obj);
+    delete t;
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,166 @@
+"""Raster: the reference's streaming rasterizer API (rendering/_raster.py:353-437) on native sm_100a kernels.
+
+Same constructor, same methods, same assertion messages.  What is behind them differs:
+
+  reference draw_triangles (:416-437)                         here
+  -------------------------------------------------------    ---------------------------------------------
+  VertexProcess -> TriangleAssembly -> (host sync) ->          ONE C-ABI call, rt_raster_draw_triangles:
+  Dehomogenize -> loop{TriangleRaster -> (host sync) ->        fused vertex/clip/setup/coverage kernel with
+  DepthTest -> FragmentProcess}; 32*W*H-fragment stream,       64-bit atomicMin on (depth<<32 | primitive),
+  >= 3 blocking read-backs and >= 5 allocations per draw       then a resolve/shade kernel; no host sync,
+                                                               no fragment stream, no per-draw allocation
+  depth buffer: W*H uint32                                     high words of the W*H uint64 key buffer
+  shaders: OpenCL C compiled at first dispatch                 tutorial shader pairs recognised by source
+                                                               fingerprint -> hand-written CUDA twins
+
+Results are bit-identical to the oracle's restatement of the reference pipeline (depth bits, winners, BGRA8).
+"""
+import hashlib
+import re
+from enum import IntEnum
+
+import numpy as np
+
+from .. import _native
+from . import _core
+from ._core import float4, create_buffer, DepthView, stream_ptr
+
+
+class FillMode(IntEnum):
+    NONE = 0
+    POINTS = 1
+    WIREFRAME = 2
+    SOLID = 3
+
+
+def shader_fingerprint(source: str) -> str:
+    """Whitespace- and comment-insensitive digest of a shader body."""
+    s = re.sub(r"/\*.*?\*/", " ", source or "", flags=re.S)
+    s = re.sub(r"//[^\n]*", " ", s)
+    s = re.sub(r"\s+", "", s)
+    return hashlib.sha256(s.encode()).hexdigest()[:16]
+
+
+# (vertex fingerprint, fragment fingerprint) -> native shader id.  Values printed by tools/shader_fingerprints.py
+# from tutorials/lesson08_rasterization.py:36-62 and tutorials/lesson09_texture_mapping.py:67-95.
+_BUILTIN_SHADERS = {
+    ("8952b904753dc90f", "b09f44910652fc57"): _native.SHADER_LESSON08,
+    ("6fc2010a5ffe2329", "ec857604fe3a70ad"): _native.SHADER_LESSON09,
+}
+
+
+def _struct_fields(dtype):
+    return [(n, dtype.fields[n][0], dtype.fields[n][1]) for n in dtype.names]
+
+
+def _check_layout(dtype, expected, what):
+    got = [(str(np.dtype(t)), off) for _, t, off in _struct_fields(dtype)]
+    want = [(str(np.dtype(t)), off) for t, off in expected]
+    if got != want:
+        raise NotImplementedError(f"{what} layout {got} does not match the built-in shader's {want}")
+
+
+class Raster:
+
+    def __init__(self, render_target, vertex_shader, vertex_shader_globals, fragment_shader, fragment_shader_globals):
+        self._render_target = render_target
+        n_pixels = render_target.width * render_target.height
+        # depth lives in the high word of a 64-bit key per pixel; starts at 0 like the reference's zero-filled
+        # uint32 buffer (:357)
+        self._key_buffer = create_buffer(n_pixels, np.uint64)
+        self._depth_buffer = DepthView(self._key_buffer, n_pixels)
+        self._fill_mode = FillMode.WIREFRAME
+        self._keys_armed = False
+
+        assert len(vertex_shader.signature) == 2 and vertex_shader.return_annotation is not None, "Vertex shader signature incorrect. Must receive one argument with vertex type and another with globals type, and return another struct"
+        assert len(fragment_shader.signature) == 2 and fragment_shader.return_annotation == float4, "Fragment shader signature incorrect. Must receive one argument with fragment type and another with globals type, and return a float4"
+        self.vertex_input_type = vertex_shader.signature[0][1].annotation
+        self.vertex_globals_type = vertex_shader.signature[1][1].annotation
+        self.vertex_output_type = vertex_shader.return_annotation
+        assert fragment_shader.signature[0][1].annotation == self.vertex_output_type, "Vertex shader output must be the same type than fragment shader input."
+        self.fragment_globals_type = fragment_shader.signature[1][1].annotation
+        self.vertex_shader = vertex_shader
+        self.fragment_shader = fragment_shader
+        self.vertex_shader_globals = vertex_shader_globals
+        self.fragment_shader_globals = fragment_shader_globals
+
+        self.shader_id = self._resolve_builtin()
+        self._records = None
+        # kept for API compatibility with code that reads them (:378-380); nothing is sized by them here
+        self.fragments_capacity = 32 * render_target.width * render_target.height
+        self.primitive_capacity = 200000
+
+    # -- shader recognition -------------------------------------------------------------------------
+    def _resolve_builtin(self):
+        key = (shader_fingerprint(self.vertex_shader.source), shader_fingerprint(self.fragment_shader.source))
+        sid = _BUILTIN_SHADERS.get(key)
+        if sid is None:
+            raise NotImplementedError(
+                f"Raster: shader pair ({self.vertex_shader.name}, {self.fragment_shader.name}) is not one of the "
+                "built-in tutorial pairs; custom OpenCL-C shaders need the NVRTC path (not available yet). "
+                "There is no CPU fallback.")
+        f4, f3, f2, m4 = _core.float4, _core.float3, _core.float2, _core.float4x4
+        _check_layout(self.vertex_input_type, [(f3, 0), (f3, 16), (f2, 32), (f3, 48), (f3, 64)], "vertex input")
+        _check_layout(self.vertex_globals_type, [(m4, 0), (m4, 64), (m4, 128)], "vertex globals")
+        if sid == _native.SHADER_LESSON08:
+            _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16)], "vertex output")
+        else:
+            _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16), (f2, 32)], "vertex output")
+            _check_layout(self.fragment_globals_type, [(_core.Texture2D, 0)], "fragment globals")
+        return sid
+
+    # -- reference accessors (:385-397) ---------------------------------------------------------------
+    def get_render_target(self):
+        return self._render_target
+
+    def get_depth_buffer(self):
+        return self._depth_buffer
+
+    @property
+    def fill_mode(self) -> FillMode:
+        return self._fill_mode
+
+    @fill_mode.setter
+    def fill_mode(self, value: FillMode):
+        self._fill_mode = value
+
+    # -- draws ------------------------------------------------------------------------------------------
+    def draw_points(self, vertex_buffer, index_buffer=None):
+        raise NotImplementedError("Raster.draw_points has no native kernel yet (SURVEY.md section 8f.3)")
+
+    def _vs_globals(self):
+        g = self.vertex_shader_globals.get()
+        names = g.dtype.names
+        return np.concatenate([np.asarray(g[n]).reshape(-1).view(np.float32)[:16] for n in names[:3]]).astype(np.float32)
+
+    def _texture_handle(self):
+        if self.shader_id != _native.SHADER_LESSON09:
+            return 0
+        g = self.fragment_shader_globals.get()
+        desc = g[g.dtype.names[0]]
+        return _core.__MEMORY_POOL__.texture_handle(int(desc["offset"]))
+
+    def draw_triangles(self, vertex_buffer, index_buffer):
+        """Raster.draw_triangles (:416-437).  index_buffer None -> triangle soup; else int32 indices.
+        Accumulates into the persistent depth / colour targets exactly like consecutive reference draws."""
+        primitive_count = (vertex_buffer.shape[0] if index_buffer is None else index_buffer.shape[0]) // 3
+        pos4, nrm4 = _core.mesh_soa(vertex_buffer)
+        idx_ptr = None
+        if index_buffer is not None:
+            assert index_buffer.dtype == np.int32, "index buffer must be int32 (_raster.py:154)"
+            idx_ptr = index_buffer.ptr
+        if not self._keys_armed:
+            # first draw on a never-cleared target: give the zero-filled key buffer its NO_PRIMITIVE low words
+            if int(self._key_buffer.version) == 0:
+                self._depth_buffer.fill(0)
+            self._keys_armed = True
+        need = _native.lib().rt_raster_record_bytes(self.shader_id, primitive_count)
+        if self._records is None or self._records.nbytes < need:
+            self._records = create_buffer(max(int(need), 16), np.uint8)
+        g = self._vs_globals()
+        rt = self._render_target
+        _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
+                     _native.float_array(g), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
+                     self._records.ptr, rt.ptr, stream_ptr())
+        self._key_buffer.device_written()
+        rt.buffer.device_written()

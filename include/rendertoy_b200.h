@@ -67,9 +67,10 @@ int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32
 /* ---- Raster.draw_triangles  (rendering/_raster.py:416-437) -----------------------------------------
  * One call = VertexProcess + TriangleAssembly(+near clip) + Dehomogenize + TriangleRaster + DepthTest
  * + FragmentProcess of the reference (kernels at _raster.py:63-73, 152-205, 118-133, 227-327, 80-93,
- * 95-112), executed as two kernels: (1) fused vertex/clip/setup/coverage with a 64-bit atomicMin on the
- * packed key, (2) resolve: re-interpolate the winning primitive per pixel, run the fragment shader once,
- * write BGRA8, re-arm the key's low word.  No host synchronisation, no intermediate fragment stream.
+ * 95-112), executed as three kernels: (1) fused vertex/clip/setup + coverage of small primitives with a
+ * 64-bit atomicMin on the packed key, (1b) coverage of large primitives from a device work queue, (2) resolve:
+ * re-interpolate the winning primitive per pixel, run the fragment shader once, write BGRA8, re-arm the key's
+ * low word.  No host synchronisation, no intermediate fragment stream.
  *
  *   d_pos4, d_nrm4   SoA vertex arrays from rt_mesh_upload_soa
  *   d_indices        int32 triangle indices or NULL for a triangle soup (_raster.py:156-158)
@@ -77,13 +78,15 @@ int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32
  *                    passed by value like the reference passes struct arguments (_core.py:270-274)
  *   tex_handle       0, or a handle from rt_texture_create (lesson09 Materials.DiffuseMap)
  *   d_key            W*H 64-bit keys (persistent across draws of a frame, like the depth buffer)
- *   d_records        scratch, >= rt_raster_record_bytes(shader, n_triangles) bytes
+ *   d_scratch        >= rt_raster_scratch_bytes(...) bytes, 16-byte aligned, ZERO-FILLED once by the caller
+ *                    (the first 256 bytes are a control block the kernels keep at zero between draws);
+ *                    holds the per-primitive setup records and the large-primitive work queue
  *   d_bgra           W*H*4 bytes, the render target
  */
-int64_t rt_raster_record_bytes(int shader, int64_t n_triangles);
+int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int height);
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles,
                              int shader, const float *vs_globals, uint64_t tex_handle, int width, int height,
-                             void *d_key, void *d_records, void *d_bgra, void *stream);
+                             void *d_key, void *d_scratch, int64_t scratch_bytes, void *d_bgra, void *stream);
 
 /* ---- textures  (rendering/_core.py:551-578 MemoryPool / create_texture2D, :94-96 sample2D) ---------
  * Point-sampled float4 CUDA texture object over caller-owned linear device memory (row 0 first).

@@ -25,8 +25,8 @@ SIGNATURES = {
     "rt_raster_clear_color": (C.c_int, [_VP, _I64, _FP, _VP]),
     "rt_raster_read_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_write_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
-    "rt_raster_record_bytes": (_I64, [_I32, _I64]),
-    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "rt_raster_scratch_bytes": (_I64, [_I32, _I64, _I32, _I32]),
+    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),
     "rt_texture_destroy": (C.c_int, [_U64]),
 }

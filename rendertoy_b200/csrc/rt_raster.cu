@@ -3,10 +3,10 @@
 //
 //   raster_kernel   one thread per input triangle: vertex shader x3, near clip into <=2 primitives,
 //                   dehomogenize, bbox + edge setup (all bit-identical to the reference arithmetic), one
-//                   64 B/96 B setup record per primitive; then the block's primitives are staged in shared
-//                   memory and their bbox cells are spread evenly over all 256 threads (prefix sum + search),
-//                   each cell doing the reference's coverage test and a 64-bit atomicMin of
-//                   (depth_bits << 32 | primitive id) into the key buffer.
+//                   64 B/96 B setup record per primitive; then each warp stages its 32 primitives in shared
+//                   memory and spreads their bbox cells evenly over its lanes, each cell doing the
+//                   reference's coverage test and a 64-bit atomicMin of (depth_bits << 32 | primitive id)
+//                   into the key buffer.
 //   resolve_kernel  one thread per pixel: decode the winning key, re-evaluate that primitive at the pixel
 //                   from its record, perspective-correct attributes, fragment shader once, BGRA8 store,
 //                   re-arm the key's low word for the next draw.
@@ -16,8 +16,6 @@
 #include "rt_common.cuh"
 
 namespace {
-
-constexpr int RB = 256; // threads per raster block = triangles per block iteration
 
 struct VO { // vertex-shader output: clip-space position + up to 3 attribute floats
     float x, y, z, w, a0, a1, a2;
@@ -145,22 +143,77 @@ __device__ __forceinline__ Cell cell_eval(const Edges &e, int col, int row)
     return c;
 }
 
+// Necessary condition for cell_eval(...).inside, without the three divisions: alpha_k = d_k / s is negative (and
+// fails alpha_k >= comp_k for comp_k in {0, 1e-8}) whenever d_k and s have strictly opposite signs, i.e. the
+// float product d_k * s is < 0.  Zeros, underflow and NaN make the product non-negative/unordered, so those
+// cells fall through to the exact test: the filter only ever rejects cells the exact test rejects.
+__device__ __forceinline__ bool cell_maybe_inside(const Edges &e, int col, int row)
+{
+    float px = (float)col + 0.5f, py = (float)row + 0.5f;
+    float d1 = e.a1 * px + e.b1 * py + e.c1;
+    float d2 = e.a2 * px + e.b2 * py + e.c2;
+    float d3 = e.a3 * px + e.b3 * py + e.c3;
+    float s = d1 + d2 + d3;
+    return !(d1 * s < 0.0f || d2 * s < 0.0f || d3 * s < 0.0f);
+}
+
 __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, float w2, float w3)
 {
     return f1 * w1 + f2 * w2 + f3 * w3;
 }
 
 // ---- kernel 1: vertex + clip + setup + coverage + depth atomics ---------------------------------
+//
+// Warp-autonomous: every warp owns 32 consecutive input triangles and never talks to another warp (no
+// __syncthreads).  After setup,
+//   * primitives with a small bbox (<= SMALL_MAX cells) are compacted into the warp's 32 shared-memory slots,
+//     their cells laid end to end, and the warp walks that list 32 cells at a time so lanes stay busy
+//     whatever the mix of sizes.  A cell finds its primitive with one warp OR-reduce + popc: owners flag the
+//     cell where their primitive starts, and a cell's slot is the number of starts at or before it;
+//   * primitives with a large bbox are NOT walked here -- one warp stuck on a few thousand cells would be the
+//     kernel's critical path.  They are cut into CHUNK-cell work items appended to a global queue
+//     (one warp-aggregated atomicAdd) that coverage_kernel drains with every warp of the machine.
+// Candidate cells (those the division-free sign test cannot reject) are compacted through a per-warp
+// shared-memory ring, so the exact test + depth atomics always run with full warps.
 
-struct Slot { // per-primitive coverage data staged in shared memory (21 words: odd stride, conflict-free)
-    float h1x, h1y, h1z, h2x, h2y, h2z, h3x, h3y, h3z;
-    float a1, b1, c1, a2, b2, c2, a3, b3, c3;
-    int sxy;       // startx | starty << 16
-    int nx_tle;    // nx | tle << 16
-    unsigned prim; // 2*t + k
+constexpr int RW = 4;           // warps per raster block
+constexpr int SMALL_MAX = 64;   // largest bbox (cells) rasterized inline by the owning warp
+constexpr int CHUNK = 128;      // cells per queued work item of a large primitive
+constexpr int RING = 64;        // per-warp candidate ring (entries)
+
+struct __align__(16) Slot { // 24 words, read as six 128-bit loads (the last two only for candidate cells)
+    float a1, b1, c1, a2;
+    float b2, c2, a3, b3;
+    float c3, inv_nx; int off; int sxy;        // sxy = startx | starty << 16
+    int nx_tle; unsigned prim; float h1x, h1y; // nx_tle = nx | tle << 16
+    float h1z, h2x, h2y, h2z;
+    float h3x, h3y, h3z, pad;
+};
+
+struct WorkCtl { // head of the scratch buffer (zero-filled by the caller once, kept at zero between draws)
+    unsigned n_items;    // queued work items of this draw (reset by resolve_kernel)
+    unsigned overflowed; // warps that had to rasterize large primitives inline because the queue was full
+    unsigned pad[2];
 };
 
 template <int SHADER> struct RecLayout { static constexpr int F4 = SHADER == RT_SHADER_LESSON08 ? 4 : 6; };
+
+// Exact coverage test + depth atomic for one cell of a primitive (h = dehomogenized vertices in edge order).
+__device__ __forceinline__ void cover_cell(const Edges &e, int col, int row, float h1x, float h1y, float h1z, float h2x,
+                                           float h2y, float h2z, float h3x, float h3y, float h3z, unsigned prim,
+                                           unsigned long long *key, int W, int H)
+{
+    Cell cl = cell_eval(e, col, row);
+    if (!cl.inside) return;
+    float hx = blend3(h1x, h2x, h3x, cl.al1, cl.al2, cl.al3);
+    float hy = blend3(h1y, h2y, h3y, cl.al1, cl.al2, cl.al3);
+    float hz = blend3(h1z, h2z, h3z, cl.al1, cl.al2, cl.al3);
+    if (hz < 0) return; // DepthTest, _raster.py:85
+    int ix = (int)hx, iy = (int)hy; // the INTERPOLATED position picks the pixel (:88-89)
+    if (ix < 0 || ix >= W || iy < 0 || iy >= H) return;
+    unsigned long long k64 = ((unsigned long long)__float_as_uint(hz) << 32) | prim;
+    atomicMin(key + (size_t)iy * W + ix, k64);
+}
 
 template <int SHADER>
 __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3, unsigned prim, Slot &s)
@@ -184,15 +237,17 @@ __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3
         r[4] = make_float4(p1.a1, p1.a2, p2.a1, p2.a2);
         r[5] = make_float4(p3.a1, p3.a2, 0.0f, 0.0f);
     }
-    s.h1x = p1.x; s.h1y = p1.y; s.h1z = p1.z;
-    s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
-    s.h3x = p3.x; s.h3y = p3.y; s.h3z = p3.z;
     s.a1 = e.a1; s.b1 = e.b1; s.c1 = e.c1;
     s.a2 = e.a2; s.b2 = e.b2; s.c2 = e.c2;
     s.a3 = e.a3; s.b3 = e.b3; s.c3 = e.c3;
+    s.inv_nx = 1.0f / (float)bb.nx;
     s.sxy = bb.startx | (bb.starty << 16);
     s.nx_tle = bb.nx | ((int)e.tle << 16);
     s.prim = prim;
+    s.h1x = p1.x; s.h1y = p1.y; s.h1z = p1.z;
+    s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
+    s.h3x = p3.x; s.h3y = p3.y; s.h3z = p3.z;
+    s.pad = 0.0f;
     return bb.nx * bb.ny;
 }
 
@@ -221,73 +276,155 @@ __device__ __forceinline__ int assemble(const DrawArgs &a, long long t, VO (&q)[
     }
 }
 
-template <int SHADER>
-__global__ void __launch_bounds__(RB) raster_kernel(const DrawArgs a)
+// Exact test for one ring entry (slot << 24 | row_local << 12 | col_local packed by the producer).
+__device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned packed, unsigned long long *key, int W, int H)
 {
-    __shared__ Slot slots[RB];
-    __shared__ int cell_off[RB + 1];
-    __shared__ int warp_tot[RB / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int W = a.width, H = a.height;
+    const float4 *sp = reinterpret_cast<const float4 *>(my_slots + (packed >> 24));
+    const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3], s4 = sp[4], s5 = sp[5];
+    const int sxy = __float_as_int(s2.w), nx_tle = __float_as_int(s3.x);
+    const int col = (sxy & 0xffff) + (int)(packed & 0xfffu), row = (sxy >> 16) + (int)((packed >> 12) & 0xfffu);
+    Edges e;
+    e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
+    e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = (unsigned)(nx_tle >> 16);
+    cover_cell(e, col, row, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, __float_as_uint(s3.y), key, W, H);
+}
 
-    for (long long base = (long long)blockIdx.x * RB; base < a.n_tris; base += (long long)gridDim.x * RB) {
-        const long long t = base + tid;
-        VO q[2][3];
-        int nprim = 0;
-        if (t < a.n_tris) nprim = assemble<SHADER>(a, t, q);
+template <int SHADER>
+__global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, const unsigned capacity)
+{
+    __shared__ Slot slots[RW][32];
+    __shared__ unsigned ring[RW][RING];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    const int W = a.width, H = a.height;
+    Slot *my_slots = slots[wid];
+    unsigned *my_ring = ring[wid];
+
+    const long long t = ((long long)blockIdx.x * RW + wid) * 32 + lane;
+    VO q[2][3];
+    int nprim = 0;
+    if (t < a.n_tris) nprim = assemble<SHADER>(a, t, q);
 
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k == 1) {
-                if (!__syncthreads_or(nprim > 1)) break; // second output triangles are rare (near-plane only)
-            }
-            int ncells = 0;
-            if (k < nprim) ncells = setup_prim<SHADER>(a, q[k][0], q[k][1], q[k][2], (unsigned)(2 * t + k), slots[tid]);
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !__any_sync(FULL, nprim > 1)) break; // second output triangles: near-plane only
+        Slot mine;
+        int ncells = 0;
+        if (k < nprim) ncells = setup_prim<SHADER>(a, q[k][0], q[k][1], q[k][2], (unsigned)(2 * t + k), mine);
 
-            // block-wide exclusive scan of ncells -> cell_off
-            int incl = ncells;
+        // large primitives -> global work queue (falls back to inline if the queue is full)
+        const unsigned big = __ballot_sync(FULL, ncells > SMALL_MAX);
+        if (big) {
+            const int nchunks = ncells > SMALL_MAX ? (ncells + CHUNK - 1) / CHUNK : 0;
+            int incl = nchunks;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, d);
+                int v = __shfl_up_sync(FULL, incl, d);
                 if (lane >= d) incl += v;
             }
-            if (lane == 31) warp_tot[wid] = incl;
-            __syncthreads();
-            int wbase = 0;
-#pragma unroll
-            for (int w = 0; w < RB / 32; ++w) wbase += (w < wid) ? warp_tot[w] : 0;
-            cell_off[tid] = wbase + incl - ncells;
-            if (tid == RB - 1) cell_off[RB] = wbase + incl;
-            __syncthreads();
-            const int total = cell_off[RB];
-
-            for (int c = tid; c < total; c += RB) {
-                int lo = 0, hi = RB; // largest p with cell_off[p] <= c
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    int mid = (lo + hi) >> 1;
-                    if (cell_off[mid] <= c) lo = mid; else hi = mid;
-                }
-                const Slot &s = slots[lo];
-                const int local = c - cell_off[lo];
-                const int nx = s.nx_tle & 0xffff;
-                const int r = (int)(((float)local + 0.5f) * __frcp_rn((float)nx)); // exact for local,nx < 4096
-                const int col = (s.sxy & 0xffff) + (local - r * nx), row = (s.sxy >> 16) + r;
-                Edges e;
-                e.a1 = s.a1; e.b1 = s.b1; e.c1 = s.c1; e.a2 = s.a2; e.b2 = s.b2; e.c2 = s.c2;
-                e.a3 = s.a3; e.b3 = s.b3; e.c3 = s.c3; e.tle = (unsigned)(s.nx_tle >> 16);
-                Cell cl = cell_eval(e, col, row);
-                if (!cl.inside) continue;
-                float hx = blend3(s.h1x, s.h2x, s.h3x, cl.al1, cl.al2, cl.al3);
-                float hy = blend3(s.h1y, s.h2y, s.h3y, cl.al1, cl.al2, cl.al3);
-                float hz = blend3(s.h1z, s.h2z, s.h3z, cl.al1, cl.al2, cl.al3);
-                if (hz < 0) continue; // DepthTest, _raster.py:85
-                int ix = (int)hx, iy = (int)hy; // the INTERPOLATED position picks the pixel (:88-89)
-                if (ix < 0 || ix >= W || iy < 0 || iy >= H) continue;
-                unsigned long long k64 = ((unsigned long long)__float_as_uint(hz) << 32) | s.prim;
-                atomicMin(a.key + (size_t)iy * W + ix, k64);
+            const int tot = __shfl_sync(FULL, incl, 31);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->n_items, (unsigned)tot);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned)tot <= capacity) {
+                unsigned w = base + (unsigned)(incl - nchunks);
+                for (int j = 0; j < nchunks; ++j) items[w + j] = make_uint2(mine.prim, (unsigned)j);
+                if (nchunks) ncells = 0; // handed over
+            } else if (lane == 0) {
+                atomicSub(&ctl->n_items, (unsigned)tot); // give the reservation back; rasterize inline below
+                atomicAdd(&ctl->overflowed, 1u);
             }
-            __syncthreads();
+        }
+
+        const unsigned nonempty = __ballot_sync(FULL, ncells > 0);
+        if (nonempty == 0) continue;
+        int incl = ncells; // inclusive warp scan of cell counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int off = incl - ncells, total = __shfl_sync(FULL, incl, 31);
+        __syncwarp(); // previous pass finished reading the slots
+        if (ncells > 0) {
+            mine.off = off;
+            my_slots[__popc(nonempty & lt_mask)] = mine;
+        }
+        __syncwarp();
+
+        int started = 0; // compacted primitives whose first cell lies before `base`
+        int pending = 0; // ring entries waiting for the exact test (warp-uniform)
+        for (int base = 0; base < total; base += 32) {
+            const unsigned rel = (unsigned)(off - base);
+            const unsigned starts = __reduce_or_sync(FULL, (ncells > 0 && rel < 32u) ? (1u << rel) : 0u);
+            const int slot = started + __popc(starts & le_mask) - 1;
+            started += __popc(starts);
+            const int c = base + lane;
+            bool cand = false;
+            unsigned packed = 0;
+            if (c < total) {
+                const float4 *sp = reinterpret_cast<const float4 *>(my_slots + slot);
+                const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                const int nx_tle = __float_as_int(sp[3].x);
+                const int local = c - __float_as_int(s2.z), sxy = __float_as_int(s2.w);
+                const int nx = nx_tle & 0xffff;
+                const int r = (int)(((float)local + 0.5f) * s2.y); // exact: local, nx < 4096
+                const int cl = local - r * nx;
+                Edges e;
+                e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
+                e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = 0;
+                cand = cell_maybe_inside(e, (sxy & 0xffff) + cl, (sxy >> 16) + r); // sign test, no division
+                packed = ((unsigned)slot << 24) | ((unsigned)r << 12) | (unsigned)cl;
+            }
+            const unsigned cm = __ballot_sync(FULL, cand);
+            if (cand) my_ring[(pending + __popc(cm & lt_mask)) & (RING - 1)] = packed;
+            pending += __popc(cm);
+            __syncwarp();
+            if (pending >= 32) { // a full warp of candidates: exact test + atomics
+                pending -= 32;
+                cover_from_slot(my_slots, my_ring[(pending + lane) & (RING - 1)], a.key, W, H);
+                __syncwarp();
+            }
+        }
+        if (lane < pending) cover_from_slot(my_slots, my_ring[lane], a.key, W, H);
+    }
+}
+
+// ---- kernel 1b: coverage of the queued large primitives ---------------------------------------------
+// Persistent grid; each warp takes whole work items (primitive, chunk) round-robin.  A lane owns CHUNK/32
+// cells of the item: it first runs the sign test on all of them, then the exact test only on survivors.
+template <int SHADER>
+__global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items)
+{
+    const unsigned n_items = ctl->n_items;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int W = a.width, H = a.height;
+    for (unsigned i = warp; i < n_items; i += n_warps) {
+        const uint2 it = items[i];
+        const float4 *r = a.rec + (size_t)it.x * RecLayout<SHADER>::F4;
+        const float4 h1 = __ldcg(r), h2 = __ldcg(r + 1), h3 = __ldcg(r + 2); // written by raster_kernel: bypass L1
+        const BBox bb = bbox_setup(h1.x, h1.y, h2.x, h2.y, h3.x, h3.y, W, H);
+        const Edges e = edge_setup(h1.x, h1.y, h2.x, h2.y, h3.x, h3.y);
+        const int ncells = bb.nx * bb.ny, first = (int)it.y * CHUNK;
+        const float inv_nx = 1.0f / (float)bb.nx;
+        unsigned cand = 0;
+        const int nj = (min(ncells - first, CHUNK) + 31) >> 5; // warp-uniform
+        for (int j = 0; j < nj; ++j) {
+            const int local = first + j * 32 + lane;
+            if (local < ncells) {
+                const int rr = (int)(((float)local + 0.5f) * inv_nx);
+                if (cell_maybe_inside(e, bb.startx + (local - rr * bb.nx), bb.starty + rr)) cand |= 1u << j;
+            }
+        }
+        while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int local = first + j * 32 + lane;
+            const int rr = (int)(((float)local + 0.5f) * inv_nx);
+            cover_cell(e, bb.startx + (local - rr * bb.nx), bb.starty + rr, h1.x, h1.y, h1.z, h2.x, h2.y, h2.z, h3.x, h3.y, h3.z,
+                       it.x, a.key, W, H);
         }
     }
 }
@@ -295,6 +432,7 @@ __global__ void __launch_bounds__(RB) raster_kernel(const DrawArgs a)
 // ---- kernel 2: resolve + fragment shader ----------------------------------------------------------
 
 struct ResolveArgs {
+    WorkCtl *ctl;
     unsigned long long *key;
     const float4 *rec;
     uint32_t *bgra;
@@ -330,7 +468,10 @@ __device__ __noinline__ bool find_source_cell(const PrimRec &p, const Edges &e, 
 template <int SHADER>
 __global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs a)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    // 256 threads cover a 32x8 pixel block; each warp an 8x4 tile, so its lanes share few primitives
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->n_items = 0; // queue drained: re-arm for the next draw
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7), y = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
     if (x >= a.width || y >= a.height) return;
     const size_t p = (size_t)y * a.width + x;
     const unsigned long long k64 = a.key[p];
@@ -420,17 +561,31 @@ struct rt_texture {
     int w, h;
 };
 
+constexpr size_t CTL_BYTES = 256;
+
 template <int SHADER>
-int launch_draw(const DrawArgs &da, const ResolveArgs &ra, cudaStream_t st)
+int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scratch_bytes, cudaStream_t st)
 {
+    // scratch = [WorkCtl, 256 B][records: 2 per triangle][work items: whatever is left]
+    char *base = (char *)scratch;
+    WorkCtl *ctl = (WorkCtl *)base;
+    const long long rec_bytes = 2 * da.n_tris * RecLayout<SHADER>::F4 * 16;
+    uint2 *items = (uint2 *)(base + CTL_BYTES + rec_bytes);
+    long long cap = (scratch_bytes - (long long)CTL_BYTES - rec_bytes) / (long long)sizeof(uint2);
+    if (cap < 0) cap = 0;
+    if (cap > 0x7fffffffll) cap = 0x7fffffffll;
+    ra.ctl = ctl;
     if (da.n_tris > 0) {
-        int per_sm = 0;
-        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel<SHADER>, RB, 0));
-        long long want = (da.n_tris + RB - 1) / RB, cap = (long long)rt_sm_count() * (per_sm > 0 ? per_sm : 1);
-        raster_kernel<SHADER><<<(int)(want < cap ? want : cap), RB, 0, st>>>(da);
+        // one warp per 32 triangles, RW warps per block; the hardware block scheduler does the load balancing
+        long long blocks = (da.n_tris + RW * 32 - 1) / (RW * 32);
+        raster_kernel<SHADER><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, (unsigned)cap);
         RT_CUDA(cudaGetLastError());
+        if (cap > 0) {
+            coverage_kernel<SHADER><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items);
+            RT_CUDA(cudaGetLastError());
+        }
     }
-    dim3 grid((ra.width + 31) / 32, (ra.height + 7) / 8), block(32, 8);
+    dim3 grid((ra.width + 31) / 32, (ra.height + 7) / 8), block(256);
     resolve_kernel<SHADER><<<grid, block, 0, st>>>(ra);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
@@ -494,18 +649,26 @@ int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32
     return RT_OK;
 }
 
-int64_t rt_raster_record_bytes(int shader, int64_t n_triangles)
+int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int height)
 {
-    int f4 = shader == RT_SHADER_LESSON08 ? 4 : 6;
-    return 2 * n_triangles * f4 * 16; // up to two primitives per input triangle
+    const int64_t f4 = shader == RT_SHADER_LESSON08 ? 4 : 6;
+    const int64_t rec = 2 * n_triangles * f4 * 16; // up to two primitives per input triangle
+    // work items: one per CHUNK cells of a large primitive.  The reference caps one pass at 32*W*H bbox cells
+    // (_raster.py:378); sized for that plus one partial chunk per primitive, bounded so huge meshes of tiny
+    // triangles do not pay for a queue they never use.  A full queue only means inline (slower) coverage.
+    int64_t items = 32ll * width * height / CHUNK + (2 * n_triangles < (1ll << 22) ? 2 * n_triangles : (1ll << 22));
+    return (int64_t)CTL_BYTES + rec + items * (int64_t)sizeof(uint2);
 }
 
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles, int shader,
-                             const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_records,
-                             void *d_bgra, void *stream)
+                             const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_scratch,
+                             int64_t scratch_bytes, void *d_bgra, void *stream)
 {
     RT_REQUIRE(n_triangles >= 0 && n_triangles < (1ll << 31), "triangle count (primitive ids are 32-bit: 2*t+k)");
-    RT_REQUIRE(n_triangles == 0 || (d_pos4 && d_nrm4 && d_records), "vertex arrays / record scratch");
+    RT_REQUIRE(n_triangles == 0 || (d_pos4 && d_nrm4), "vertex arrays");
+    RT_REQUIRE(d_scratch && ((uintptr_t)d_scratch & 15) == 0, "scratch buffer (16-byte aligned)");
+    RT_REQUIRE(scratch_bytes >= (int64_t)CTL_BYTES + 2 * n_triangles * (shader == RT_SHADER_LESSON08 ? 4 : 6) * 16,
+               "scratch buffer too small: see rt_raster_scratch_bytes");
     RT_REQUIRE(vs_globals && d_key && d_bgra, "globals / targets");
     RT_REQUIRE(width > 0 && height > 0 && width <= 32768 && height <= 32768, "viewport");
     RT_REQUIRE(shader == RT_SHADER_LESSON08 || shader == RT_SHADER_LESSON09, "shader id");
@@ -514,17 +677,18 @@ int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32
     for (int i = 0; i < 48; ++i) da.g[i] = vs_globals[i];
     da.width = width; da.height = height;
     da.half_w = (float)width * 0.5f; da.half_h = (float)height * 0.5f; // viewport_dim * 0.5f, _raster.py:129
-    da.key = (unsigned long long *)d_key; da.rec = (float4 *)d_records;
+    da.key = (unsigned long long *)d_key; da.rec = (float4 *)((char *)d_scratch + CTL_BYTES);
     ResolveArgs ra;
+    ra.ctl = nullptr;
     ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
     ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
     if (shader == RT_SHADER_LESSON09) {
         RT_REQUIRE(tex_handle != 0, "lesson09 shader needs a texture handle");
         const rt_texture *t = (const rt_texture *)(uintptr_t)tex_handle;
         ra.tex = t->obj; ra.tex_w = t->w; ra.tex_h = t->h;
-        return launch_draw<RT_SHADER_LESSON09>(da, ra, (cudaStream_t)stream);
+        return launch_draw<RT_SHADER_LESSON09>(da, ra, d_scratch, scratch_bytes, (cudaStream_t)stream);
     }
-    return launch_draw<RT_SHADER_LESSON08>(da, ra, (cudaStream_t)stream);
+    return launch_draw<RT_SHADER_LESSON08>(da, ra, d_scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int rt_texture_create(const void *d_texels, int width, int height, uint64_t *out_handle)

@@ -85,7 +85,7 @@ class Raster:
         self.fragment_shader_globals = fragment_shader_globals
 
         self.shader_id = self._resolve_builtin()
-        self._records = None
+        self._scratch = None
         # kept for API compatibility with code that reads them (:378-380); nothing is sized by them here
         self.fragments_capacity = 32 * render_target.width * render_target.height
         self.primitive_capacity = 200000
@@ -154,13 +154,13 @@ class Raster:
             if int(self._key_buffer.version) == 0:
                 self._depth_buffer.fill(0)
             self._keys_armed = True
-        need = _native.lib().rt_raster_record_bytes(self.shader_id, primitive_count)
-        if self._records is None or self._records.nbytes < need:
-            self._records = create_buffer(max(int(need), 16), np.uint8)
-        g = self._vs_globals()
         rt = self._render_target
+        need = _native.lib().rt_raster_scratch_bytes(self.shader_id, primitive_count, rt.width, rt.height)
+        if self._scratch is None or self._scratch.nbytes < need:
+            self._scratch = create_buffer(int(need), np.uint8)   # zero-filled: the control block starts armed
+        g = self._vs_globals()
         _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
                      _native.float_array(g), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
-                     self._records.ptr, rt.ptr, stream_ptr())
+                     self._scratch.ptr, self._scratch.nbytes, rt.ptr, stream_ptr())
         self._key_buffer.device_written()
         rt.buffer.device_written()

@@ -98,25 +98,28 @@ int rt_texture_destroy(uint64_t handle);
  * The reference ships only the skeleton (ray_cast is `pass`); semantics are defined in
  * oracle/raycast_oracle.c.  LBVH: 30-bit Morton codes of triangle centroids -> LSD radix sort ->
  * Karras hierarchy -> bottom-up AABB refit; traversal is a persistent-thread stack walk. */
-int64_t rt_bvh_node_bytes(int64_t n_triangles);    /* bytes of d_nodes  */
-int64_t rt_bvh_tri_bytes(int64_t n_triangles);     /* bytes of d_tris   */
-int64_t rt_bvh_scratch_bytes(int64_t n_triangles); /* bytes of d_scratch (build only) */
-/* Raycaster._build_ads (rendering/_raycaster.py:30-33). d_tri_ids (uint32[n]) receives the original
- * triangle id of each sorted leaf. */
+int64_t rt_bvh_node_bytes(int64_t n_triangles);    /* bytes of d_nodes   (64 B inner nodes)            */
+int64_t rt_bvh_tri_bytes(int64_t n_triangles);     /* bytes of d_tris    (48 B leaf triangles, sorted) */
+int64_t rt_bvh_scratch_bytes(int64_t n_triangles); /* bytes of d_scratch (build only)                  */
+/* Raycaster._build_ads (rendering/_raycaster.py:30-33).  d_pos4 as for the rasterizer; triangle ids are
+ * positions in the (optionally indexed) triangle list. */
 int rt_bvh_build(const void *d_pos4, const int32_t *d_indices, int64_t n_triangles, void *d_nodes, void *d_tris,
-                 void *d_tri_ids, void *d_scratch, void *stream);
-/* Raycaster.ray_cast (rendering/_raycaster.py:35-36): rays = n x {float3 origin, float3 dir} (32 B),
- * hits = n x {float t, uint32 triangle, float u, float v} (16 B); miss: t = +inf, triangle = 0xFFFFFFFF. */
-int rt_raycast_rays(const void *d_nodes, const void *d_tris, const void *d_tri_ids, int64_t n_triangles,
-                    const void *d_rays, int64_t n_rays, void *d_hits, void *stream);
+                 void *d_scratch, void *stream);
+/* Raycaster.ray_cast (rendering/_raycaster.py:35-36): rays = n x {float3 origin, float3 dir} (32 B, OpenCL
+ * float3 padding), hits = n x {float t, uint32 triangle, float u, float v} (16 B); miss: t = +inf,
+ * triangle = 0xFFFFFFFF.  d_ctl: 256-byte control block, ZERO-FILLED once by the caller (the kernel re-arms it). */
+int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_rays, int64_t n_rays,
+                    void *d_hits, void *d_ctl, void *stream);
 /* Fused primary-ray generation + closest hit + Lambert/texture shade for the pixel rect
  * [x0,x0+w) x [y0,y0+h) of a width x height frame.  camera = {origin, U, V, W} (12 floats, model space,
- * HOST memory): dir = (U*sx + V*sy) + W.  Outputs are rect-local, row-major: d_hits (16 B/pixel, may be
- * NULL), d_bgra (4 B/pixel, pitch `bgra_pitch_px` pixels so a rank can write straight into a frame). */
-int rt_raycast_primary(const void *d_nodes, const void *d_tris, const void *d_tri_ids, int64_t n_triangles,
+ * HOST memory): dir = (U*sx + V*sy) + W with (sx, sy) the NDC pixel centre.  Outputs are rect-local,
+ * row-major: d_hits (16 B/pixel, may be NULL), d_bgra (4 B/pixel, may be NULL; row pitch `bgra_pitch_px`
+ * pixels, so a rank can write its tile straight into a full frame).  shader selects the lesson08 / lesson09
+ * shading; d_pos4 / tex_handle are only needed for lesson09. */
+int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
-                       int64_t bgra_pitch_px, void *stream);
+                       int64_t bgra_pitch_px, void *d_ctl, void *stream);
 
 #ifdef __cplusplus
 }

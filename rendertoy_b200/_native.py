@@ -27,6 +27,13 @@ SIGNATURES = {
     "rt_raster_write_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_scratch_bytes": (_I64, [_I32, _I64, _I32, _I32]),
     "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _VP]),
+    "rt_bvh_node_bytes": (_I64, [_I64]),
+    "rt_bvh_tri_bytes": (_I64, [_I64]),
+    "rt_bvh_scratch_bytes": (_I64, [_I64]),
+    "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
+    "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
+                                     _I64, _VP, _VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),
     "rt_texture_destroy": (C.c_int, [_U64]),
 }

@@ -32,6 +32,12 @@ void rt_set_error(const char *fmt, ...);
 
 int rt_sm_count();
 
+// handle returned by rt_texture_create
+struct rt_texture {
+    cudaTextureObject_t obj;
+    int w, h;
+};
+
 // normalize((float3)(1,1,1)).x, correctly rounded (lesson08:42)
 #define RT_INV_SQRT3 0.57735026918962576f
 

@@ -556,11 +556,6 @@ int fill_grid(long long n_vec)
     return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
-struct rt_texture {
-    cudaTextureObject_t obj;
-    int w, h;
-};
-
 constexpr size_t CTL_BYTES = 256;
 
 template <int SHADER>

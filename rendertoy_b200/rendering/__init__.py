@@ -19,4 +19,6 @@ from ._presentation import create_presenter, Presenter, Event
 
 from ._raster import Raster
 
-from . import _core, _modeling, _loaders, _presentation, _raster
+from ._raycaster import Raycaster
+
+from . import _core, _modeling, _loaders, _presentation, _raster, _raycaster

@@ -1,0 +1,186 @@
+"""Raycaster: closest-hit ray casting over triangle meshes (reference: rendering/_raycaster.py).
+
+The reference declares the API and nothing else: BVH_AABB / BVH_Triangle structs (:8-22), a constructor whose
+_build_ads() computes a triangle count and drops it (:30-33) and `ray_cast(rays) -> pass` (:35-36).  The names,
+the struct fields and the (models) / (rays) signatures are kept; the behaviour is new and is defined by
+oracle/raycast_oracle.c (float32 Moller-Trumbore, closest hit by (t bits, triangle id), two-sided):
+
+  _build_ads()   GPU LBVH over all triangles of all models (rt_bvh_build: Morton codes -> radix sort ->
+                 Karras hierarchy -> refit), mesh data replicated per GPU
+  ray_cast(rays) rays: buffer of Ray {origin: float3, direction: float3}; returns a buffer of
+                 RayHit {t, index, mesh, u, v} (miss: t = +inf, index = mesh = -1)
+  render(...)    the fused hot path: primary rays of a camera for a pixel rect -> hits and/or shaded BGRA8
+                 written straight into a render target (Lambert of lesson08:42 or texture of lesson09:90-95)
+"""
+import typing
+
+import numpy as np
+import torch
+
+from .. import _native
+from . import _core
+from ._core import kernel_struct, float3, create_buffer, stream_ptr, DeviceBuffer
+from ._modeling import Mesh
+
+
+@kernel_struct
+class BVH_AABB:
+    min: float3
+    max: float3
+    count: int
+    elements: int
+
+
+@kernel_struct
+class BVH_Triangle:
+    v0: float3
+    v1: float3
+    v2: float3
+    index: int
+    mesh: int
+
+
+@kernel_struct
+class Ray:
+    origin: float3
+    direction: float3
+
+
+@kernel_struct
+class RayHit:
+    t: np.float32
+    index: np.int32
+    mesh: np.int32
+    u: np.float32
+    v: np.float32
+
+
+def camera_frame(view, proj, world=None):
+    """{origin, U, V, W} (12 float32, model space) of the reference camera convention (rendering/_core.py:
+    528-548): a pixel centre with NDC coordinates (sx, sy) looks along U*sx + V*sy + W.
+    view/proj/world: float4x4 values (or 4x4 arrays), row-vector convention.  Computed in float64, rounded once."""
+    def m(x):
+        x = np.asarray(x)
+        if x.dtype == _core.float4x4:
+            x = _core.to_array(x)
+        return np.asarray(x, dtype=np.float64).reshape(4, 4)
+    view, proj = m(view), m(proj)
+    r = view[0:3, 0:3]                                  # columns: xaxis, yaxis, zaxis
+    eye = -(view[3, 0:3] @ np.linalg.inv(r))
+    u, v, w = r[:, 0] / proj[0, 0], r[:, 1] / proj[1, 1], r[:, 2]
+    if world is not None:
+        winv = np.linalg.inv(m(world))
+        eye = (np.append(eye, 1.0) @ winv)[:3]
+        u, v, w = ((np.append(x, 0.0) @ winv)[:3] for x in (u, v, w))
+    return np.concatenate([eye, u, v, w]).astype(np.float32)
+
+
+class Raycaster:
+    def __init__(self, models: typing.List[Mesh]):
+        self.models = models
+        self._build_ads()
+
+    def _build_ads(self):
+        pos, nrm, idx, counts = [], [], [], []
+        vbase = 0
+        any_indexed = False
+        for m in self.models:
+            m: Mesh
+            p4, n4 = _core.mesh_soa(m.vertices)
+            nverts = m.vertices.shape[0]
+            # only int32 index buffers are real (the kernels' [np.int32], _raster.py:154); load_obj's never-filled
+            # `int` buffer (_loaders.py:17) is treated like the tutorials treat it: ignored
+            use_idx = m.indices is not None and m.indices.dtype == np.int32
+            triangles = nverts // 3 if not use_idx else m.indices.shape[0] // 3
+            if use_idx:
+                any_indexed = True
+                i32 = m.indices.tensor().view(torch.int32)[:triangles * 3]
+            else:
+                i32 = None
+            pos.append(p4[:nverts]); nrm.append(n4[:nverts]); idx.append((i32, vbase, triangles)); counts.append(triangles)
+            vbase += nverts
+        self.tri_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.n_triangles = int(self.tri_offsets[-1])
+        assert self.n_triangles >= 1, "Raycaster needs at least one triangle"
+        if len(self.models) == 1:
+            self.pos4, self.nrm4 = pos[0], nrm[0]
+            self.indices = idx[0][0]
+        else:
+            self.pos4, self.nrm4 = torch.cat(pos), torch.cat(nrm)
+            if any_indexed:
+                parts = []
+                for i32, base, tris in idx:
+                    parts.append((i32 if i32 is not None else torch.arange(tris * 3, dtype=torch.int32, device=self.pos4.device)) + base)
+                self.indices = torch.cat(parts).to(torch.int32)
+            else:
+                self.indices = None
+        dev = self.pos4.device
+        L = _native.lib()
+        n = self.n_triangles
+        self.nodes = torch.empty(int(L.rt_bvh_node_bytes(n)), dtype=torch.uint8, device=dev)
+        self.tris = torch.empty(int(L.rt_bvh_tri_bytes(n)), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(int(L.rt_bvh_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+        self.ctl = torch.zeros(256, dtype=torch.uint8, device=dev)
+        _native.call("rt_bvh_build", self.pos4.data_ptr(), self._idx_ptr(), n, self.nodes.data_ptr(), self.tris.data_ptr(),
+                     scratch.data_ptr(), stream_ptr())
+        self._build_scratch = scratch  # kept until the stream has consumed it
+
+    def _idx_ptr(self):
+        return None if self.indices is None else self.indices.data_ptr()
+
+    # -- generic rays ---------------------------------------------------------------------------------
+    def ray_cast_native(self, rays: DeviceBuffer) -> torch.Tensor:
+        """(n, 4) float32 tensor {t, triangle id bits, u, v} with GLOBAL triangle ids (no mesh split)."""
+        n = rays.size
+        assert rays.dtype.itemsize == 32, "rays must be Ray {origin: float3, direction: float3} (32 bytes)"
+        hits = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.pos4.device)
+        _native.call("rt_raycast_rays", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, rays.ptr, n,
+                     hits.data_ptr(), self.ctl.data_ptr(), stream_ptr())
+        return hits[:n]
+
+    def ray_cast(self, rays: DeviceBuffer) -> DeviceBuffer:
+        native = self.ray_cast_native(rays)
+        n = native.shape[0]
+        out = create_buffer(n, RayHit)
+        t = out.tensor().view(torch.float32).view(n, 5)
+        gid = native[:, 1].contiguous().view(torch.int32).to(torch.int64)
+        miss = gid < 0  # 0xFFFFFFFF
+        offs = torch.as_tensor(self.tri_offsets, device=native.device)
+        mesh = torch.searchsorted(offs, gid.clamp(min=0), right=True) - 1
+        index = gid - offs[mesh]
+        mesh = torch.where(miss, torch.full_like(mesh, -1), mesh)
+        index = torch.where(miss, torch.full_like(index, -1), index)
+        t[:, 0] = native[:, 0]
+        t[:, 1] = index.to(torch.int32).view(torch.float32)
+        t[:, 2] = mesh.to(torch.int32).view(torch.float32)
+        t[:, 3] = native[:, 2]
+        t[:, 4] = native[:, 3]
+        out.device_written()
+        return out
+
+    # -- fused primary rays -----------------------------------------------------------------------------
+    def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
+               hits: torch.Tensor = None, frame_size=None):
+        """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
+        shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
+        hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
+        hits are wanted (then frame_size=(W, H) is required)."""
+        if render_target is not None:
+            W, H = render_target.width, render_target.height
+        else:
+            W, H = frame_size
+        x0, y0, w, h = rect if rect is not None else (0, 0, W, H)
+        tex = 0
+        if shader == _native.SHADER_LESSON09:
+            desc = texture_descriptor.get() if hasattr(texture_descriptor, "get") else texture_descriptor
+            tex = _core.__MEMORY_POOL__.texture_handle(int(desc["offset"]))
+        bgra_ptr = None
+        if render_target is not None:
+            assert render_target.is_bgra8, "render target must be the BGRA8 presenter image"
+            bgra_ptr = render_target.ptr + 4 * (y0 * W + x0)
+        _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
+                     self.nrm4.data_ptr(), self._idx_ptr(), _native.float_array(np.asarray(camera, np.float32).reshape(12)),
+                     W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
+                     self.ctl.data_ptr(), stream_ptr())
+        if render_target is not None:
+            render_target.buffer.device_written()

@@ -1,0 +1,499 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of rendertoy_b200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--path raycast|raster]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+BASELINE.json's metric has two halves; each is measured on the config it is quoted on, one JSON line:
+
+  primary    "Mrays/s closest-hit (dragon, 4K)"  -> configs[3]: dragon100k, 3840x2160, lesson06 camera orbit,
+             fused primary rays + closest hit + Lambert shade, frames split across ranks, gathered to rank 0
+  secondary  "Mtris/s raster"                    -> configs[1]: dragon100k, 1920x1080, lesson08 shaders,
+             clear + clear + draw_triangles per frame (reported under "secondary" in the same line)
+
+A step = FRAMES_PER_RANK frames per rank of the orbit animation (weak scaling: per-GPU work is fixed).
+`value` = device-timed whole-job throughput with mesh/BVH resident; `e2e` = the same work driven through the
+public `rendering` API with host-side inputs and every frame read back to pinned host memory.
+`--impl reference` times the CPU oracle (oracle/: the restated reference pipeline; the reference has no ray
+caster, so that half is our CPU BVH definition) on the host cores -- it is a baseline, not the target.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRIS = 100_000
+RAY_W, RAY_H = 3840, 2160
+RAS_W, RAS_H = 1920, 1080
+FRAMES_PER_RANK = 8
+ORBIT = 256  # World = rotate(2*pi*k/256, y)  
+
+METRIC_RAY = "Mrays/s closest-hit (dragon, 4K)"
+METRIC_RAS = "Mtris/s raster"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes from the committed ncu --set full captures (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while a timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scene helpers
+# ---------------------------------------------------------------------------------------------------------
+
+def orbit_t(k):
+    return 2.0 * math.pi * (k % ORBIT) / ORBIT
+
+
+def make_mesh(ren):
+    from rendertoy_b200 import scenes
+    rows = scenes.dragon(N_TRIS)
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    return rows, vb
+
+
+def ray_camera(ren, k):
+    from rendering._raycaster import camera_frame
+    from rendertoy_b200 import scenes
+    world, view, proj = scenes.lesson_camera(ren, 6, orbit_t(k), RAY_W, RAY_H)
+    return camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+
+
+def dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primary: ray casting, configs[3]
+# ---------------------------------------------------------------------------------------------------------
+
+def bench_raycast(args, rank, world):
+    import torch
+    import rendering as ren
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200 import parallel
+    from rendertoy_b200._native import SHADER_LESSON08
+
+    rows, vb = make_mesh(ren)
+    rc = Raycaster([ren.Mesh(vb, None)])
+    F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
+    my_frames = parallel.frame_indices(n_frames, rank, world)
+    targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]     # F x 33 MB > L2
+    local = torch.empty((F, RAY_H, RAY_W), dtype=torch.int32, device="cuda")
+    gathered = torch.empty((n_frames, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
+    cams = {k: ray_camera(ren, k) for k in range(n_frames * (args.steps + args.warmup))}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * args.steps)]
+
+    def step(s, timed_idx=None):
+        for j, k in enumerate(my_frames):
+            if timed_idx is not None:
+                ev[timed_idx * F + j][0].record()
+            rc.render(targets[j], cams[s * n_frames + k])
+            if timed_idx is not None:
+                ev[timed_idx * F + j][1].record()
+        if world > 1:   # the only collective: finished frames -> rank 0
+            for j in range(F):
+                local[j].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W))
+            parallel.gather_frames(local, gathered, n_frames)
+
+    for s in range(args.warmup):
+        step(s)
+    sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step(args.warmup + s, timed_idx=s)
+    e1.record()
+    barrier_sync(world)
+    clocks = sampler.result()
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    rays_total = RAY_W * RAY_H * n_frames * args.steps
+    value = rays_total / (ms * 1e-3) / 1e6
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # instrumented pass (outside the timed region): node visits / triangle tests per ray
+    stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+    rc.render(targets[0], cams[my_frames[0]], stats=stats)
+    torch.cuda.synchronize()
+    nodes, tests, rays = (int(x) for x in stats.cpu())
+
+    # ---- e2e: public API, host inputs, every frame read back to pinned host memory
+    host = [torch.empty((RAY_H, RAY_W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    done = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    from rendertoy_b200 import scenes
+    from rendering._raycaster import camera_frame
+
+    def e2e_step(s):
+        for j, k in enumerate(my_frames):
+            world_m, view, proj = scenes.lesson_camera(ren, 6, orbit_t(s * n_frames + k), RAY_W, RAY_H)   # host inputs
+            cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world_m, dtype=ren.float4x4))
+            rc.render(targets[j], cam)
+            done[j % 2].record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[j % 2])
+                host[j % 2].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W), non_blocking=True)
+        if world > 1:
+            for j in range(F):
+                local[j].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W))
+            parallel.gather_frames(local, gathered, n_frames)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+
+    e2e_step(0)
+    barrier_sync(world)
+    k_e2e = max(2, min(args.steps, 5))
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for s in range(k_e2e):
+        e2e_step(1 + s)
+    g1.record()
+    barrier_sync(world)
+    e2e_ms = max_over_ranks(g0.elapsed_time(g1), world)
+    e2e_value = RAY_W * RAY_H * n_frames * k_e2e / (e2e_ms * 1e-3) / 1e6
+
+    hbm_peak, peak_src = peaks()
+    alg_bytes = 12 * RAY_W * RAY_H + N_TRIS * 96 + (2 * N_TRIS - 1) * 32
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    sm_count = torch.cuda.get_device_properties(0).multi_processor_count
+    fp32_peak = sm_count * 128 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
+    flops = (nodes * 2 * 22 + tests * 45) * (RAY_W * RAY_H / max(rays, 1))
+    out = {
+        "metric": METRIC_RAY, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[3]: dragon100k (synthetic stand-in for the missing dragon.obj, 100000 triangles) "
+                               "raycast 3840x2160, lesson06 camera orbit, primary rays + closest hit + Lambert shade",
+                   "frames_per_rank_per_step": F, "partition": "frames k = rank (mod N), framebuffers gathered to rank 0 (NCCL)",
+                   "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
+                         "L2-resident by design, as they are reused every frame",
+                   "bvh_build_excluded": True},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": ncu_traffic().get("raycast_kernel"), "peak_source": peak_src,
+                     "kernel": "raycast_kernel<8>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "HBM does not bind this kernel (BVH is L2-resident); the binding units are the FP32 pipe and "
+                             "L1/L2 latency, see fp32 and profiles/",
+                     "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
+                              "inner_node_visits_per_ray": nodes / max(rays, 1), "triangle_tests_per_ray": tests / max(rays, 1),
+                              "flop_model": "44 flop per inner node (2 slab tests) + 45 flop per Moller-Trumbore test; peak counts "
+                                            "FMA as 2 flop, this kernel is compiled -fmad=false for bit-exact parity"}},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": 4 * RAY_W * RAY_H * F,
+                "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async D2H of the "
+                                        "33 MB BGRA8 frame into pinned memory (PCIe-bound)"},
+        "gpu_launches": F * args.steps, "clocks": clocks,
+    }
+    return out, rows
+
+
+# ---------------------------------------------------------------------------------------------------------
+# secondary: rasterization, configs[1]
+# ---------------------------------------------------------------------------------------------------------
+
+def bench_raster(args, rank, world, rows=None):
+    import torch
+    import rendering as ren
+    from rendertoy_b200 import lessons, scenes, parallel
+
+    if rows is None:
+        rows, vb = make_mesh(ren)
+    else:
+        vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+        with ren.mapped(vb) as m:
+            m.view(np.float32).reshape(rows.shape)[:] = rows
+    F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
+    my_frames = parallel.frame_indices(n_frames, rank, world)
+    # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
+    rasters = []
+    for _ in range(F):
+        pres = ren.create_presenter(RAS_W, RAS_H)
+        rasters.append(lessons.build_lesson08(ren, pres.get_render_target()))
+    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda")
+    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
+    cams = {k: scenes.lesson_camera(ren, 8, orbit_t(k), RAS_W, RAS_H) for k in range(n_frames * (args.steps + args.warmup + 6))}
+
+    def frame(j, k):
+        raster, g = rasters[j]
+        lessons.set_transforms(ren, g, *cams[k])
+        lessons.render_frame(ren, raster, vb)
+
+    def gather():
+        if world > 1:
+            for j in range(F):
+                local[j].copy_(rasters[j][0].get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W))
+            parallel.gather_frames(local, gathered, n_frames)
+
+    def step(s):
+        for j, k in enumerate(my_frames):
+            frame(j, s * n_frames + k)
+        gather()
+
+    for s in range(args.warmup):
+        step(s)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    e1.record()
+    barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    tris_total = N_TRIS * n_frames * args.steps
+    value = tris_total / (ms * 1e-3) / 1e6
+    frame_ms = ms / (args.steps * F)
+
+    host = [torch.empty((RAS_H, RAS_W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_step(s):
+        for j, k in enumerate(my_frames):
+            raster, g = rasters[j]
+            cam = scenes.lesson_camera(ren, 8, orbit_t(s * n_frames + k), RAS_W, RAS_H)      # host matrices every frame
+            lessons.set_transforms(ren, g, *cam)
+            lessons.render_frame(ren, raster, vb)
+            done[j % 2].record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[j % 2])
+                host[j % 2].copy_(raster.get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W), non_blocking=True)
+        gather()
+        torch.cuda.current_stream().wait_stream(copy_stream)
+
+    e2e_step(args.steps + args.warmup)
+    barrier_sync(world)
+    k_e2e = max(2, min(args.steps, 5))
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for s in range(k_e2e):
+        e2e_step(args.steps + args.warmup + 1 + s)
+    g1.record()
+    barrier_sync(world)
+    e2e_ms = max_over_ranks(g0.elapsed_time(g1), world)
+    hbm_peak, peak_src = peaks()
+    alg_bytes = 3 * N_TRIS * 32 + RAS_W * RAS_H * 20                               # SURVEY.md section 8(d), per frame
+    achieved = alg_bytes / (frame_ms * 1e-3) / 1e9
+    return {
+        "metric": METRIC_RAS, "value": value, "unit": "Mtris/s", "ms_per_step": ms / args.steps,
+        "config": {"workload": "configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders, clear + clear + draw_triangles per frame",
+                   "frames_per_rank_per_step": F, "l2": "8 independent raster targets per rank (~300 MB of key/colour/record buffers > L2)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": ncu_traffic().get("raster_frame"), "peak_source": peak_src, "unit_of_work": "one frame = 5 kernels "
+                     "(2 clears, raster_kernel, coverage_kernel, resolve_kernel); algorithmic bytes are defined per frame",
+                     "frame_ms": frame_ms, "algorithmic_bytes_per_frame": alg_bytes},
+        "e2e": {"value": N_TRIS * n_frames * k_e2e / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": 192 * F,
+                "d2h_bytes_per_step": 4 * RAS_W * RAS_H * F, "steps": k_e2e},
+        "gpu_launches": 5 * F * args.steps,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+
+_CPU_BVH = {}
+
+
+def cpu_raycast(rows, n_frames, first=0, min_seconds=0.0):
+    """CPU BVH closest hit + shade for >= n_frames 4K frames (until min_seconds); returns (Mrays/s, seconds, frames).
+    The BVH build is excluded, as on the GPU side."""
+    import oracle
+    from oracle import host_math as hm
+    if id(rows) not in _CPU_BVH:
+        _CPU_BVH[id(rows)] = oracle.bvh_build(rows)
+    bvh = _CPU_BVH[id(rows)]
+    t0 = time.perf_counter()
+    k = first
+    while k < first + n_frames or time.perf_counter() - t0 < min_seconds:
+        W = hm.matmul(hm.scale(1.0), hm.rotate(orbit_t(k), (0, 1, 0)))
+        V = hm.look_at((0, 0.3, 2), (0, 0, 0), (0, 1, 0))
+        P = hm.perspective(aspect_ratio=RAY_W / RAY_H)
+        cam = hm.camera_frame(V, P, W)
+        rays = oracle.primary_rays(cam, RAY_W, RAY_H)
+        t, ids, u, v = oracle.bvh_raycast(bvh, rays)
+        oracle.shade_hits(8, rows, ids, u, v)
+        k += 1
+    dt = time.perf_counter() - t0
+    return RAY_W * RAY_H * (k - first) / dt / 1e6, dt, k - first
+
+
+def cpu_raster(rows, n_frames, first=0, min_seconds=0.0):
+    import oracle
+    from oracle import host_math as hm
+    t0 = time.perf_counter()
+    k = first
+    while k < first + n_frames or time.perf_counter() - t0 < min_seconds:
+        W = hm.matmul(hm.scale(1.0), hm.rotate(orbit_t(k), (0, 1, 0)))
+        V = hm.look_at((0, 0.3, 1.0), (0, 0, 0), (0, 1, 0))
+        P = hm.perspective(aspect_ratio=RAS_W / RAS_H)
+        oracle.draw_triangles(8, RAS_W, RAS_H, rows, np.concatenate([W.ravel(), V.ravel(), P.ravel()]))
+        k += 1
+    dt = time.perf_counter() - t0
+    return N_TRIS * (k - first) / dt / 1e6, dt, k - first
+
+
+def reference_arm(args):
+    """Times the CPU oracle on this box's host cores, same metric/config as our arm."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import oracle
+    from rendertoy_b200 import scenes
+    oracle.build()
+    rows = scenes.dragon(N_TRIS)
+    cores = oracle.num_threads()
+    fn, metric, unit, sample = (cpu_raster, METRIC_RAS, "Mtris/s", "1 frame of 1920x1080 x 100000 triangles per step") \
+        if args.path == "raster" else (cpu_raycast, METRIC_RAY, "Mrays/s", "1 frame of 3840x2160 (8.29 Mrays) per step")
+    fn(rows, 1, 0)   # builds the CPU BVH (excluded, as on the GPU side) and faults everything in
+    for s in range(args.warmup):
+        fn(rows, 1, s)
+    t0 = time.perf_counter()
+    vals = [fn(rows, 1, args.warmup + s)[0] for s in range(args.steps)]
+    wall = time.perf_counter() - t0
+    units = (RAY_W * RAY_H if args.path != "raster" else N_TRIS) * args.steps
+    value = units / wall / 1e6
+    kind_note = ("oracle port of the reference pipeline (rendering/_raster.py kernels restated in C + OpenMP; pyopencl is not installable here)"
+                 if args.path == "raster" else
+                 "CPU BVH of oracle/raycast_oracle.c: the reference has NO ray caster (rendering/_raycaster.py:35-36 is `pass`)")
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": ("configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders" if args.path == "raster" else
+                                "configs[3]: dragon100k raycast 3840x2160, lesson06 camera orbit, closest hit + Lambert shade"),
+                   "note": kind_note},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "per_step": vals,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="raycast", choices=["raycast", "raster"], help="which half of the metric is the primary line")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (rendertoy_b200 has no CPU path); use --impl reference for the CPU oracle")
+    rank, world, local = dist_setup(args.gpus)
+    ray, rows = bench_raycast(args, rank, world)
+    ras = bench_raster(args, rank, world, rows)
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            cores = oracle.num_threads()
+            cpu_raycast(rows, 1)
+            v, dt, nf = cpu_raycast(rows, 2, min_seconds=10.0)
+            ray["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                   "sample": f"{nf} frames of 3840x2160 ({nf * RAY_W * RAY_H / 1e6:.1f} Mrays) in {dt:.1f} s; CPU BVH of "
+                                             "oracle/raycast_oracle.c (the reference has no ray caster)"}
+            cpu_raster(rows, 1)
+            v, dt, nf = cpu_raster(rows, 8, min_seconds=10.0)
+            ras["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": cores, "kind": "port",
+                                   "sample": f"{nf} frames of 1920x1080 x 100000 triangles in {dt:.1f} s; restated reference pipeline "
+                                             "(oracle/raster_oracle.c, OpenMP)"}
+        primary, secondary = (ray, ras) if args.path == "raycast" else (ras, ray)
+        if args.path == "raster":
+            for k in ("n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "clocks"):
+                primary.setdefault(k, ray.get(k))
+        primary["secondary"] = secondary
+        print(json.dumps(primary))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

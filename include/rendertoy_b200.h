@@ -115,11 +115,12 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * HOST memory): dir = (U*sx + V*sy) + W with (sx, sy) the NDC pixel centre.  Outputs are rect-local,
  * row-major: d_hits (16 B/pixel, may be NULL), d_bgra (4 B/pixel, may be NULL; row pitch `bgra_pitch_px`
  * pixels, so a rank can write its tile straight into a full frame).  shader selects the lesson08 / lesson09
- * shading; d_pos4 / tex_handle are only needed for lesson09. */
+ * shading; d_pos4 / tex_handle are only needed for lesson09.  d_stats: NULL, or 3 x uint64 that an instrumented
+ * build of the kernel ADDS {inner-node visits, triangle tests, rays} to (for the roofline report; slower). */
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
-                       int64_t bgra_pitch_px, void *d_ctl, void *stream);
+                       int64_t bgra_pitch_px, void *d_ctl, void *d_stats, void *stream);
 
 #ifdef __cplusplus
 }

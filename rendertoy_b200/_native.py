@@ -33,7 +33,7 @@ SIGNATURES = {
     "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
-                                     _I64, _VP, _VP]),
+                                     _I64, _VP, _VP, _VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),
     "rt_texture_destroy": (C.c_int, [_U64]),
 }

@@ -37,18 +37,22 @@ struct TraceArgs {
     cudaTextureObject_t tex;
     int tex_w, tex_h;
     unsigned *ctl; // [0] next work unit, [1] finished blocks; both zero between launches
+    unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
 
 struct Hit { float t, u, v; unsigned id; };
 
+template <bool STATS>
 __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, float oz, float dx, float dy, float dz, int *stack /* [STACK][TB] column */)
 {
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
     unsigned long long best = ~0ull;
     float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
     int sp = 0, cur = 0;
+    unsigned n_nodes = 0, n_tests = 0;
     for (;;) {
         if (cur >= 0) {
+            if (STATS) ++n_nodes;
             const float4 *np = reinterpret_cast<const float4 *>(a.nodes + cur);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             const int4 n3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -72,6 +76,7 @@ __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, flo
             if (h0) { cur = n3.x; continue; }
             if (h1) { cur = n3.y; continue; }
         } else {
+            if (STATS) ++n_tests;
             const float4 *tp = reinterpret_cast<const float4 *>(a.tris + ~cur);
             const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
             // Moller-Trumbore, operation for operation as oracle/raycast_oracle.c: rc_moller_trumbore
@@ -97,6 +102,11 @@ __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, flo
         if (sp == 0) break;
         --sp;
         cur = stack[sp * TB];
+    }
+    if (STATS) {
+        atomicAdd(a.stats, (unsigned long long)n_nodes);
+        atomicAdd(a.stats + 1, (unsigned long long)n_tests);
+        atomicAdd(a.stats + 2, 1ull);
     }
     Hit h;
     h.t = tbest; h.u = bu; h.v = bv; h.id = best == ~0ull ? 0xFFFFFFFFu : (unsigned)best;
@@ -127,7 +137,7 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 }
 
 // MODE 0: rays from a buffer, hits out.  MODE 8 / 9: primary rays + shade with that lesson's shader.
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
 {
     __shared__ int stack_mem[STACK * TB];
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
             const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
             const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
             const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
-            const Hit h = trace(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+            const Hit h = trace<STATS>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
             const long long p = (long long)ly * a.w + lx;
             if (a.hits) a.hits[p] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
             if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
             const long long r = (long long)unit * 32 + lane;
             if (r >= a.n_rays) continue;
             const float4 o = __ldg(a.rays + 2 * r), d = __ldg(a.rays + 2 * r + 1);
-            const Hit h = trace(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
+            const Hit h = trace<STATS>(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
             a.hits[r] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
         }
     }
@@ -172,14 +182,20 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
     }
 }
 
+template <int MODE, bool STATS>
+int launch_trace_s(const TraceArgs &a, cudaStream_t st)
+{
+    int per_sm = 0;
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<MODE, STATS>, TB, 0));
+    raycast_kernel<MODE, STATS><<<rt_sm_count() * (per_sm > 0 ? per_sm : 1), TB, 0, st>>>(a);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
 template <int MODE>
 int launch_trace(const TraceArgs &a, cudaStream_t st)
 {
-    int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<MODE>, TB, 0));
-    raycast_kernel<MODE><<<rt_sm_count() * (per_sm > 0 ? per_sm : 1), TB, 0, st>>>(a);
-    RT_CUDA(cudaGetLastError());
-    return RT_OK;
+    return a.stats ? launch_trace_s<MODE, true>(a, st) : launch_trace_s<MODE, false>(a, st);
 }
 
 } // namespace
@@ -202,7 +218,8 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
 
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4, const void *d_nrm4,
                        const int32_t *d_indices, const float *camera, int width, int height, int x0, int y0, int w, int h, int shader,
-                       uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_ctl, void *stream)
+                       uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_ctl, void *d_stats,
+                       void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
     RT_REQUIRE(camera && d_ctl, "camera / control block");
@@ -217,6 +234,7 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     a.width = width; a.height = height; a.x0 = x0; a.y0 = y0; a.w = w; a.h = h;
     a.hits = (float4 *)d_hits; a.bgra = (uint32_t *)d_bgra; a.pitch_px = bgra_pitch_px;
     a.pos = (const float4 *)d_pos4; a.nrm = (const float4 *)d_nrm4; a.idx = d_indices; a.ctl = (unsigned *)d_ctl;
+    a.stats = (unsigned long long *)d_stats;
     if (shader == RT_SHADER_LESSON09) {
         RT_REQUIRE(!d_bgra || (tex_handle != 0 && d_pos4), "lesson09 shading needs a texture handle and positions");
         if (tex_handle) {

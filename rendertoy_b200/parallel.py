@@ -1,0 +1,81 @@
+"""Multi-GPU partitioning for the two hot paths (the reference is single-device,
+rendering/_core.py:10-11).
+
+One process per GPU (torchrun), mesh + BVH replicated on every rank, no data-path exchange except ONE
+collective: finished BGRA8 framebuffer pieces are gathered to rank 0 (NCCL over NVLink; gloo in CPU tests).
+
+  tile_rects(W, H, rank, world)        image-space partition of one large frame: 8-aligned row bands, round-robin
+  frame_indices(n_frames, rank, world) animation batches: rank r renders frames k = r (mod world)
+  gather_tiles / gather_frames         the collective (grouped isend/irecv, i.e. ncclSend/ncclRecv: NCCL has no
+                                       native gather)
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+BAND = 64  # rows per band: multiple of the traversal's 8x4 warp tile, small enough to balance a frame
+
+
+def tile_rects(width: int, height: int, rank: int, world: int, band: int = BAND) -> List[Tuple[int, int, int, int]]:
+    """(x0, y0, w, h) row bands owned by `rank`: band b belongs to rank b % world.  Bands interleave so every
+    rank sees a similar mix of background and mesh."""
+    rects = []
+    for b, y0 in enumerate(range(0, height, band)):
+        if b % world == rank:
+            rects.append((0, y0, width, min(band, height - y0)))
+    return rects
+
+
+def frame_indices(n_frames: int, rank: int, world: int) -> List[int]:
+    return list(range(rank, n_frames, world))
+
+
+def _is_dist():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def gather_tiles(frame: torch.Tensor, width: int, height: int, band: int = BAND, dst: int = 0):
+    """frame: (H, W) int32/uint8x4 tensor holding this rank's bands at their final positions.  After the call
+    rank `dst` holds every band.  Each band is one send/recv, all grouped in a single batch."""
+    if not _is_dist():
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    for b, y0 in enumerate(range(0, height, band)):
+        owner = b % world
+        rows = frame[y0:min(y0 + band, height)]
+        if owner == dst:
+            continue
+        if rank == owner:
+            ops.append(dist.P2POp(dist.isend, rows, dst))
+        elif rank == dst:
+            ops.append(dist.P2POp(dist.irecv, rows, owner))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def gather_frames(local_frames: torch.Tensor, all_frames: torch.Tensor, n_frames: int, dst: int = 0):
+    """Animation batch: local_frames (n_local, H, W) holds frames rank, rank+world, ...; all_frames
+    (n_frames, H, W) on rank `dst` receives every frame at its index."""
+    if not _is_dist():
+        if all_frames is not None and all_frames.data_ptr() != local_frames.data_ptr():
+            all_frames[:local_frames.shape[0]].copy_(local_frames)
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops = []
+    if rank == dst:
+        for j, k in enumerate(frame_indices(n_frames, dst, world)):
+            all_frames[k].copy_(local_frames[j])
+        for src in range(world):
+            if src == dst:
+                continue
+            for k in frame_indices(n_frames, src, world):
+                ops.append(dist.P2POp(dist.irecv, all_frames[k], src))
+    else:
+        for j, _ in enumerate(frame_indices(n_frames, rank, world)):
+            ops.append(dist.P2POp(dist.isend, local_frames[j], dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()

@@ -160,11 +160,12 @@ class Raycaster:
 
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
-               hits: torch.Tensor = None, frame_size=None):
+               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None):
         """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
         shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
         hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
-        hits are wanted (then frame_size=(W, H) is required)."""
+        hits are wanted (then frame_size=(W, H) is required).  stats: optional int64[3] tensor; the instrumented kernel
+        adds {node visits, triangle tests, rays} to it."""
         if render_target is not None:
             W, H = render_target.width, render_target.height
         else:
@@ -181,6 +182,6 @@ class Raycaster:
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
                      self.nrm4.data_ptr(), self._idx_ptr(), _native.float_array(np.asarray(camera, np.float32).reshape(12)),
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
-                     self.ctl.data_ptr(), stream_ptr())
+                     self.ctl.data_ptr(), None if stats is None else stats.data_ptr(), stream_ptr())
         if render_target is not None:
             render_target.buffer.device_written()

@@ -1,0 +1,198 @@
+"""Host-side logic of the `rendering` mirror (no GPU): dtype layouts, matrices, buffers, loaders, shader
+recognition, and the C ABI's symbol table."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from rendertoy_b200 import _native, lessons, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_public_names_match_reference_init(ren):
+    names = """kernel_main kernel_struct create_buffer_from create_buffer create_struct mapped kernel_function create_struct_from
+        create_image2d Image Buffer r_image1d_t w_image1d_t r_image2d_t w_image2d_t r_image3d_t w_image3d_t make_float2 make_float3
+        make_float4 make_float4x4 translate identity scale rotate matmul to_array clear perspective look_at normalize dot float2
+        float3 float4 int2 int3 int4 uint2 uint3 uint4 float4x4 Texture2D create_texture2D Mesh WeldMode SubdivisionMode MeshVertex
+        manifold load_obj create_presenter Presenter Event Raster""".split()
+    for n in names:                                   # rendering/__init__.py:1-15
+        assert hasattr(ren, n), n
+    import rendering._raster, rendering._core, rendering._raycaster   # import-by-path used by reference callers
+    assert rendering._raster.FillMode.SOLID == 3 and hasattr(rendering._core, "make_int2") and hasattr(rendering._core, "cross")
+
+
+def test_struct_layouts(ren):
+    """SURVEY.md appendix B (OpenCL layout rules)."""
+    mv = ren.MeshVertex
+    assert mv.itemsize == 80 and [mv.fields[n][1] for n in "PNCTB"] == [0, 16, 32, 48, 64]
+    assert ren.float3.itemsize == 16 and ren.float4x4.itemsize == 64 and ren.float2.itemsize == 8
+    assert ren.Texture2D.itemsize == 12
+
+    @ren.kernel_struct
+    class Transforms:
+        World: ren.float4x4
+        View: ren.float4x4
+        Proj: ren.float4x4
+
+    @ren.kernel_struct
+    class VO8:
+        proj: ren.float4
+        C: ren.float3
+
+    @ren.kernel_struct
+    class VO9:
+        proj: ren.float4
+        L: ren.float3
+        C: ren.float2
+
+    assert Transforms.itemsize == 192 and VO8.itemsize == 32 and VO9.itemsize == 48
+    assert VO9.fields["C"][1] == 32
+    from rendering._raycaster import BVH_AABB, BVH_Triangle
+    assert BVH_AABB.itemsize == 48 and BVH_Triangle.itemsize == 64      # `int` -> int64 on Linux
+
+
+def test_matrices_bitwise_equal_oracle_restatement(ren, oracle):
+    hm = oracle.host_math
+    f3 = ren.make_float3
+    for eye in ((0, 0.3, 1.0), (0, 0.3, 2), (1.5, -0.7, 0.4)):
+        a = ren.to_array(ren.look_at(f3(*eye), f3(0, 0, 0), f3(0, 1, 0)))
+        assert np.array_equal(a.view(np.uint32), hm.look_at(eye, (0, 0, 0), (0, 1, 0)).view(np.uint32))
+    for asp in (1.0, 640 / 480, 1920 / 1080, 3840 / 2160):
+        assert np.array_equal(ren.to_array(ren.perspective(aspect_ratio=asp)).view(np.uint32), hm.perspective(aspect_ratio=asp).view(np.uint32))
+    for t in (0.0, 0.5, 2.1, 6.0):
+        w = np.array(ren.matmul(ren.scale(1.0), ren.rotate(t, f3(0, 1, 0))), dtype=ren.float4x4)
+        assert np.array_equal(ren.to_array(w).view(np.uint32), hm.matmul(hm.scale(1.0), hm.rotate(t, (0, 1, 0))).view(np.uint32))
+    ax = ren.normalize(f3(1, 2, 3))
+    assert np.array_equal(ren.to_array(ren.rotate(0.7, ax)).view(np.uint32), hm.rotate(0.7, ren.to_array(ax)).view(np.uint32))
+    assert isinstance(ren.matmul(ren.identity(), ren.identity()), tuple)     # reference returns .item() tuples here
+    assert ren.dot(f3(1, 2, 3), f3(4, 5, 6)) == 32.0
+    assert np.allclose(ren.to_array(ren.translate(1, 2, 3))[3, :3], (1, 2, 3))
+
+
+def test_buffers_structs_clear_and_views(ren):
+    b = ren.create_buffer(10, np.float32)
+    assert b.shape == (10,) and (b.get() == 0).all()
+    with ren.mapped(b) as m:
+        m[:] = np.arange(10)
+    assert (b.get() == np.arange(10)).all() and (b[2:5].get() == [2, 3, 4]).all() and len(b) == 10
+    ren.clear(b, 1.0)
+    assert (b.get().view(np.uint32) == 0x3F800000).all()
+    s = ren.create_struct(ren.Texture2D)
+    with ren.mapped(s) as m:
+        m["width"] = 7
+    assert s.shape == () and int(s.get()["width"]) == 7
+    big = ren.create_buffer(100_000, ren.float4)            # no host shadow at this size
+    with ren.mapped(big) as m:
+        m["x"] = 3.0
+    assert (big.get()["x"] == 3.0).all() and big.view(np.float32).shape == (400_000,)
+    c = ren.create_buffer_from(np.arange(6, dtype=np.int32))
+    assert int(c[5:6].map_to_host()[0]) == 5
+    mem, desc = ren.create_texture2D(5, 3)
+    assert mem.shape == (3, 5) and mem.dtype == ren.float4 and int(desc.get()["width"]) == 5 and int(desc.get()["height"]) == 3
+    _, desc2 = ren.create_texture2D(2, 2)
+    assert int(desc2.get()["offset"]) % 512 == 0 and int(desc2.get()["offset"]) >= 5 * 3 * 16
+
+
+def test_manifold(ren):
+    m = ren.manifold(4, 3)
+    v = m.vertices.get()
+    assert m.vertices.shape == (20,) and m.indices.shape == (4 * 3 * 6,) and m.indices.dtype == np.int32
+    rows = v.view(np.float32).reshape(-1, 20)
+    assert np.allclose(rows[6, 0:3], (0.25, 1 / 3, 0.0)) and np.allclose(rows[:, 8:10], rows[:, 0:2])
+    idx = m.indices.get()
+    assert list(idx[:6]) == [0, 1, 5, 1, 2, 6] and list(idx[12:18]) == [0, 5, 4, 1, 6, 5]      # row stride `slices` quirk kept
+    with pytest.raises(Exception, match="Not implemented yet"):
+        m.clone()
+
+
+def test_load_obj_roundtrip(ren, tmp_path):
+    rows = scenes.dragon(300, normalise=False)
+    path = tmp_path / "mini.obj"
+    scenes.write_obj(str(path), rows, with_uv=True)
+    (mesh, material), = ren.load_obj(str(path))
+    assert material is None and mesh.vertices.shape == (rows.shape[0],)
+    got = mesh.vertices.get().view(np.float32).reshape(-1, 20)
+    want = scenes.normalise_like_load_obj(np.loadtxt([f"{r[0]:.9g} {r[1]:.9g} {r[2]:.9g}" for r in rows], dtype=np.float32).reshape(-1, 3).copy())
+    assert np.array_equal(got[:, 0:3], want[:, 0:3]) if want.shape[1] >= 3 else True
+    assert np.allclose(got[:, 4:7], rows[:, 4:7], atol=1e-6) and np.allclose(got[:, 8:10], rows[:, 8:10], atol=1e-6)
+    assert got[:, 0:3].min() == -0.5 and mesh.indices.shape == (rows.shape[0],) and (mesh.indices.get() == 0).all()
+    # quads fan-triangulate, negative indices resolve
+    q = tmp_path / "quad.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf -4//1 -3//1 -2//1 -1//1\n")
+    (mesh2, _), = ren.load_obj(str(q))
+    p = mesh2.vertices.get().view(np.float32).reshape(-1, 20)[:, 0:3] + 0.5
+    assert p.shape[0] == 6 and np.allclose(p[[0, 1, 2, 3, 4, 5]], [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 0, 0), (1, 1, 0), (0, 1, 0)])
+
+
+def test_raster_recognises_tutorial_shaders_and_rejects_others(ren):
+    pres = ren.create_presenter(32, 16)
+    raster, g = lessons.build_lesson08(ren, pres.get_render_target())
+    assert raster.shader_id == _native.SHADER_LESSON08 and raster.get_depth_buffer().shape == (512,)
+    tex = np.zeros((4, 4, 3), np.uint8)
+    raster9, *_ = lessons.build_lesson09(ren, pres.get_render_target(), tex)
+    assert raster9.shader_id == _native.SHADER_LESSON09
+
+    @ren.kernel_struct
+    class VOut:
+        proj: ren.float4
+        C: ren.float3
+
+    @ren.kernel_function
+    def vs(vertex: ren.MeshVertex, info: ren.float4x4) -> VOut:
+        """
+        VOut o; o.proj = (float4)(vertex.P, 1); o.C = vertex.N; return o;
+        """
+
+    @ren.kernel_function
+    def fs(fragment: VOut, info: ren.float4x4) -> ren.float4:
+        """
+        return (float4)(fragment.C, 1);
+        """
+
+    with pytest.raises(NotImplementedError):
+        ren.Raster(pres.get_render_target(), vs, ren.create_struct(ren.float4x4), fs, ren.create_struct(ren.float4x4))
+    with pytest.raises(AssertionError, match="Fragment shader signature incorrect"):
+        ren.Raster(pres.get_render_target(), vs, None, vs, None)
+    with pytest.raises(Exception, match="Can not call to this function from host"):
+        vs()
+
+
+def test_presenter_is_headless_and_bounded(ren, monkeypatch):
+    monkeypatch.setenv("RENDERTOY_B200_FRAMES", "2")
+    p = ren.create_presenter(8, 4)
+    n = 0
+    while True:
+        ev, _ = p.poll_events()
+        if ev == ren.Event.CLOSED:
+            break
+        p.present()
+        n += 1
+    assert n == 2 and p.get_render_target().shape == (8, 4)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """include/rendertoy_b200.h <-> librendertoy_b200.so <-> ctypes table."""
+    header = open(os.path.join(ROOT, "include", "rendertoy_b200.h")).read()
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rt_status"}
+    lib = _native.lib()                      # loads without a GPU
+    exported = set(re.findall(r" T (rt_\w+)", subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout))
+    assert declared, "no declarations parsed"
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    assert declared == set(_native.SIGNATURES), f"ctypes table out of sync: {sorted(declared ^ set(_native.SIGNATURES))}"
+    assert lib.rt_abi_version() == 1
+    assert lib.rt_raster_scratch_bytes(8, 1000, 64, 64) > 2 * 1000 * 64 and lib.rt_bvh_node_bytes(1000) == 999 * 64
+
+
+def test_kernels_fail_loudly_without_cuda(ren):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    pres = ren.create_presenter(32, 16)
+    raster, g = lessons.build_lesson08(ren, pres.get_render_target())
+    vb = ren.create_buffer(3, ren.MeshVertex)
+    with pytest.raises(Exception):
+        raster.draw_triangles(vb, None)       # no CPU fallback: the native call refuses

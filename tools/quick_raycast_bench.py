@@ -1,0 +1,41 @@
+"""Dev-time: time BVH build and fused primary-ray render at 4K / 1080p."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import rendering as ren
+from rendering._raycaster import Raycaster, camera_frame
+from rendertoy_b200 import scenes
+
+def cam(lesson, t, w, h):
+    world, view, proj = scenes.lesson_camera(ren, lesson, t, w, h)
+    return camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+
+def run(n_tris, w, h, lesson, frames=20):
+    rows = scenes.dragon(n_tris)
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    rc = Raycaster([ren.Mesh(vb, None)])
+    torch.cuda.synchronize(); tb = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); rc._build_ads(); e1.record(); torch.cuda.synchronize()
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    cams = [cam(lesson, 0.1 * k, w, h) for k in range(frames)]
+    for k in range(3): rc.render(target, cams[k])
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(frames): rc.render(target, cams[k])
+    f1.record(); torch.cuda.synchronize()
+    ms = f0.elapsed_time(f1) / frames
+    cov = (target.get()[:, :, 3] != 0).mean()
+    print(f"T={rows.shape[0]//3} {w}x{h} lesson{lesson:02d}: build {e0.elapsed_time(e1)*1e3:.0f} us (first {tb*1e3:.1f} ms), render {ms*1e3:.1f} us/frame -> {w*h/ms/1e3:.1f} Mrays/s, coverage {cov:.3f}")
+
+if __name__ == "__main__":
+    fr = 3 if len(sys.argv) > 1 and sys.argv[1] == "ncu" else 20
+    run(100_000, 3840, 2160, 6, fr)
+    run(100_000, 3840, 2160, 8, fr)
+    if fr > 3:
+        run(100_000, 1920, 1080, 8, fr)
+        run(1_000_000, 3840, 2160, 6, fr)

@@ -22,7 +22,7 @@ class _Config(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("triangles_in", "primitives", "skipped_z0", "dropped_large", "fragments",
-                                        "fragments_offscreen", "tie_pixels", "pixels_written")]
+                                        "fragments_offscreen", "tie_pixels", "pixels_written", "over_capacity")]
 
 
 def build(force=False):

@@ -1,0 +1,51 @@
+"""oracle/clshim/build_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Recipe run by __graft_entry__.build() when /root/reference is present: imports the unmodified reference package
+through fake_cl, instantiates its Raster with the lesson08 and lesson09 tutorial shaders (one process each, as
+the reference keeps one global OpenCL program per process) and compiles the resulting OpenCL C program text
+for the host CPU.  Outputs: oracle/_ref/clprog_*.{cpp,so} (git-ignored).  Reference sources are read where they
+lie; nothing is copied into the repo.  tests/golden/*.npz are produced by make_golden.py from these programs.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get("RENDERTOY_REFERENCE", "/root/reference")
+
+CHILD = r'''
+import sys
+sys.path.insert(0, {repo!r})
+sys.argv = ["make_golden"]
+import importlib.util
+spec = importlib.util.spec_from_file_location("mg", {mg!r})
+mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+ren = mg.ren
+lesson = {lesson}
+ns = mg.tutorial_definitions({ref!r} + "/tutorials/lesson%02d_" % lesson + ("rasterization.py" if lesson == 8 else "texture_mapping.py"))
+target = ren.create_image2d(64, 48, ren._core.RGBA)
+g = ren.create_struct(ns["Transforms"])
+fg = g if lesson == 8 else ren.create_struct(ns["Materials"])
+ren.Raster(target, ns["transform_and_draw"], g, ns["fragment_to_color"], fg)
+import pyopencl as cl
+prog = cl.Program(ren._core.__ctx__, ren._core.__code__).build()
+print("lesson%02d: %d kernels compiled from the reference's program text" % (lesson, len(prog.kernels)))
+'''
+
+
+def main():
+    if not os.path.isdir(REFERENCE):
+        print("reference checkout not present; nothing to build")
+        return 0
+    for f in glob.glob(os.path.join(REPO, "oracle", "_ref", "clprog_*")):
+        os.remove(f)
+    for lesson in (8, 9):
+        code = CHILD.format(repo=REPO, mg=os.path.join(HERE, "make_golden.py"), ref=REFERENCE, lesson=lesson)
+        subprocess.check_call([sys.executable, "-c", code], cwd="/tmp")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,182 @@
+"""oracle/clshim/make_golden.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Generates tests/golden/raster_*.npz by running the UNMODIFIED reference (`/root/reference/rendering`, its
+Raster class, its generated OpenCL C kernels and the tutorial shaders read verbatim from
+tutorials/lesson08_rasterization.py / lesson09_texture_mapping.py) on the CPU through fake_cl, and checks
+oracle/raster_oracle.c against every case while doing so.  This is what pins the oracle.
+
+    python oracle/clshim/make_golden.py            # needs /root/reference; writes tests/golden/
+
+What the shim substitutes (and nothing else): the OpenCL runtime (kernels compiled by g++ through
+cl_compat.hpp, strict float32, work-items run in global-id order) and the host matrices (the reference's
+look_at/normalize raise under NumPy 2; oracle/host_math.py supplies them).
+"""
+import ast
+import os
+import signal
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFERENCE = os.environ.get("RENDERTOY_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+
+import oracle                                    # noqa: E402
+from oracle import host_math as hm               # noqa: E402
+from oracle.clshim import fake_cl                # noqa: E402
+from rendertoy_b200 import scenes                # noqa: E402  (numpy-only mesh generator)
+
+fake_cl.install()
+# the repo root holds a drop-in `rendering` alias package; the reference must win here
+sys.path.insert(0, REFERENCE)
+for k in [k for k in sys.modules if k == "rendering" or k.startswith("rendering.")]:
+    del sys.modules[k]
+import rendering as ren                          # noqa: E402  -- the reference itself
+assert ren.__file__.startswith(REFERENCE), ren.__file__
+
+
+def tutorial_definitions(path):
+    """exec the @kernel_struct classes and @kernel_function shaders of a tutorial, verbatim, nothing else."""
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.decorator_list]
+    ns = {"ren": ren, "np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def upload_mesh(rows):
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    return vb
+
+
+def set_globals(buf, W, V, P):
+    with ren.mapped(buf) as m:
+        m["World"] = ren.make_float4x4(np.ascontiguousarray(W, np.float32))
+        m["View"] = ren.make_float4x4(np.ascontiguousarray(V, np.float32))
+        m["Proj"] = ren.make_float4x4(np.ascontiguousarray(P, np.float32))
+
+
+def read_targets(raster, target):
+    depth = raster.get_depth_buffer().get().copy()
+    with ren.mapped(target) as m:
+        bgra = np.array(m).view(np.uint8).copy()
+    return depth.reshape(target.height, target.width), bgra.reshape(target.height, target.width, 4)
+
+
+class Timeout(Exception):
+    pass
+
+
+def _alarm(*_):
+    raise Timeout()
+
+
+def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=None, out_dir=None):
+    """One frame: clear, clear, then one draw per entry of rows_list (draws compose on the same targets)."""
+    lesson_file = f"{REFERENCE}/tutorials/lesson{lesson:02d}_" + ("rasterization.py" if lesson == 8 else "texture_mapping.py")
+    ns = tutorial_definitions(lesson_file)
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    W, V, P = hm.matmul(hm.scale(1.0), hm.rotate(t, (0, 1, 0))), hm.look_at(eye, (0, 0, 0), (0, 1, 0)), hm.perspective(aspect_ratio=w / h)
+    texf = None
+    if lesson == 8:
+        g = ren.create_struct(ns["Transforms"])
+        raster = ren.Raster(target, ns["transform_and_draw"], g, ns["fragment_to_color"], g)
+    else:
+        th, tw = texture.shape[0], texture.shape[1]
+        mem, desc = ren.create_texture2D(tw, th)
+        with ren.mapped(mem) as m:
+            m = m.view(np.float32).ravel().reshape(th, tw, 4)
+            m[:, :, 0:3] = texture / 255.0
+            m[:, :, 3] = 1.0
+            texf = np.array(m)
+        g = ren.create_struct(ns["Transforms"])
+        fg = ren.create_struct(ns["Materials"])
+        raster = ren.Raster(target, ns["transform_and_draw"], g, ns["fragment_to_color"], fg)
+        with ren.mapped(fg) as m:
+            m["DiffuseMap"] = desc.get()
+    set_globals(g, W, V, P)
+    ren.clear(raster.get_render_target())
+    ren.clear(raster.get_depth_buffer(), 1.0)
+    indices_list = indices_list or [None] * len(rows_list)
+    signal.signal(signal.SIGALRM, _alarm)
+    signal.alarm(120)
+    try:
+        for rows, idx in zip(rows_list, indices_list):
+            ib = None if idx is None else ren.create_buffer_from(np.asarray(idx, np.int32))
+            raster.draw_triangles(upload_mesh(rows), ib)
+    except Timeout:
+        print(f"{name}: reference did not terminate (latent hang of the `while` at _raster.py:428); case skipped")
+        return None
+    finally:
+        signal.alarm(0)
+    depth, bgra = read_targets(raster, target)
+
+    # the oracle on the same inputs
+    gl = np.concatenate([W.ravel(), V.ravel(), P.ravel()]).astype(np.float32)
+    od, ob, tie_any = None, None, np.zeros((h, w), np.uint8)
+    stats = []
+    for rows, idx in zip(rows_list, indices_list):
+        r = oracle.draw_triangles(lesson, w, h, rows, gl, indices=idx, texture=texf, depth=od, bgra=ob)
+        od, ob = r.depth, r.bgra
+        tie_any |= r.tie
+        stats.append(r.stats)
+    depth_bad = int((od != depth).sum())
+    colour_bad = (ob != bgra).any(axis=-1)
+    colour_bad_notie = int((colour_bad & (tie_any == 0)).sum())
+    covered = int((depth != 0x3F800000).sum())
+    print(f"{name}: {w}x{h} draws={len(rows_list)} covered={covered} depth_mismatch={depth_bad} colour_mismatch={int(colour_bad.sum())} "
+          f"(outside depth ties: {colour_bad_notie}) tie_pixels={int(tie_any.sum())} stats={stats}")
+    if out_dir:
+        np.savez_compressed(os.path.join(out_dir, f"raster_{name}.npz"), lesson=lesson, width=w, height=h, globals=gl,
+                            n_draws=len(rows_list), texture=texf if texf is not None else np.zeros(0, np.float32),
+                            depth=depth, bgra=bgra, tie=tie_any,
+                            **{f"rows{i}": r for i, r in enumerate(rows_list)},
+                            **{f"indices{i}": (np.asarray(ix, np.int32) if ix is not None else np.zeros(0, np.int32)) for i, ix in enumerate(indices_list)})
+    return depth_bad, colour_bad_notie
+
+
+def cases():
+    rng = np.random.default_rng(7)
+    tex = rng.integers(0, 256, size=(17, 23, 3), dtype=np.uint8)
+    a, b = scenes.dragon(600), scenes.dragon(500, seed=3)
+    b[:, 0:3] = b[:, 0:3] * np.float32(0.8) + np.float32(0.05)
+    perm = rng.permutation(b.shape[0] // 3)
+    idx = np.arange(b.shape[0], dtype=np.int32).reshape(-1, 3)[perm].ravel()
+    return {
+        # lesson08 camera, small dragon
+        "l08_dragon2k": dict(lesson=8, rows_list=[scenes.dragon(2000)], w=160, h=120, eye=(0, 0.3, 1.0), t=0.5),
+        # lesson09 texture path
+        "l09_dragon1k": dict(lesson=9, rows_list=[scenes.dragon(1200)], w=200, h=150, eye=(0, 0.3, 1.0), t=1.3, texture=tex),
+        # lesson06 camera (further away: sub-pixel triangles), odd viewport
+        "l08_far_odd": dict(lesson=8, rows_list=[scenes.dragon(3000)], w=97, h=61, eye=(0, 0.3, 2), t=2.1),
+        # camera inside the knot: triangles cross the near plane (clip codes 1..6, second output triangles), some
+        # bboxes reach the 64*64 drop.  Camera chosen by screening with the oracle (stats skipped_z0 == 0 and
+        # over_capacity == 0): most clipping cameras make the reference's `while` at _raster.py:428 spin forever,
+        # either on a clipped primitive whose first vertex gets z<0 (:236) or on an off-screen primitive whose two
+        # negative bbox extents multiply to >= 32*W*H (:241, :245).
+        "l08_nearclip": dict(lesson=8, rows_list=[scenes.dragon(800)], w=128, h=96, eye=(0.12, 0.32, 0.3), t=4.5),
+        "l09_nearclip": dict(lesson=9, rows_list=[scenes.dragon(800)], w=128, h=96, eye=(0.12, 0.32, 0.3), t=4.5, texture=tex),
+        # two draws composing on one depth/colour target, the second one indexed
+        "l08_two_draws_indexed": dict(lesson=8, rows_list=[a, b], w=144, h=108, eye=(0, 0.3, 1.0), t=0.9, indices_list=[None, idx]),
+    }
+
+
+def main():
+    """Each case runs in its own process: the reference accumulates one global OpenCL program per process
+    (rendering/_core.py `__code__`), exactly one tutorial's worth."""
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        r = run_case(sys.argv[2], out_dir=out_dir, **cases()[sys.argv[2]])
+        return 0 if r is None or (r[0] == 0 and r[1] == 0) else 1
+    import subprocess
+    bad = [n for n in cases() if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
+    print("ORACLE PINNED: every depth word and every non-tie colour matches the reference run" if not bad else f"MISMATCH in {bad}")
+    return 0 if not bad else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

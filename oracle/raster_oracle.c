@@ -11,7 +11,8 @@
  * rounded division.  Build with -O2 -ffp-contract=off -fno-fast-math.
  *
  * Pinning: checked against the reference's own kernel strings executed through
- * oracle/clshim (see oracle/README.md) -> tests/golden/.
+ * oracle/clshim (see oracle/README.md) -> tests/golden/: every depth word and colour byte of six
+ * reference-run scenes is reproduced (tests/test_golden.py).
  *
  * Reference citations are relative to /root/reference/.
  */
@@ -38,12 +39,15 @@ typedef struct {
 typedef struct {
     int64_t triangles_in;
     int64_t primitives;        /* visible_primitives, _raster.py:424 */
-    int64_t skipped_z0;        /* primitives dropped by "already rendered" test, _raster.py:236 */
+    int64_t skipped_z0;        /* primitives dropped by "already rendered" test, _raster.py:236; never counted as drawn:
+                                  the reference's `while` at :428 then never terminates */
     int64_t dropped_large;     /* pixel_count >= 64*64, _raster.py:294 */
     int64_t fragments;         /* out_fragments, _raster.py:433 */
     int64_t fragments_offscreen; /* (int)proj.xy outside the target: reference behaviour undefined */
     int64_t tie_pixels;        /* pixels where >1 primitive produced the winning depth bits */
     int64_t pixels_written;
+    int64_t over_capacity;     /* primitives whose pixel_count >= 32*W*H (two negative bbox extents multiply to a large
+                                  positive count, :241): :245 never admits them, so the reference loops forever */
 } orc_stats;
 
 /* ---- vertex-out layout ------------------------------------------------------
@@ -181,7 +185,7 @@ static void orc_fragbuf_push(orc_fragbuf *fb, const float *f, int st, uint32_t p
 
 /* _raster.py:227-327 TriangleRaster for one primitive (three dehomogenized vertices) */
 static void orc_raster_one(const float *P, int st, int W, int H, uint32_t prim_id, orc_fragbuf *fb,
-                           int64_t *skipped_z0, int64_t *dropped_large)
+                           int64_t *skipped_z0, int64_t *dropped_large, int64_t *over_capacity)
 {
     const float *v1 = P, *v2 = P + st, *v3 = P + 2 * st;
     if (v1[2] < 0) { (*skipped_z0)++; return; } /* :236 "already rendered" */
@@ -190,6 +194,7 @@ static void orc_raster_one(const float *P, int st, int W, int H, uint32_t prim_i
     int64_t endx = 1 + (int64_t)orc_f2i(fmaxf(v1[0], fmaxf(v2[0], v3[0]))); if (endx > W - 1) endx = W - 1;
     int64_t endy = 1 + (int64_t)orc_f2i(fmaxf(v1[1], fmaxf(v2[1], v3[1]))); if (endy > H - 1) endy = H - 1;
     int64_t pixel_count = (endx - startx + 1) * (endy - starty + 1);
+    if (pixel_count >= 32ll * W * H) (*over_capacity)++;
 
     float ax = v1[0], ay = v1[1], bx = v2[0], by = v2[1], cx = v3[0], cy = v3[1];
     float e1x = bx - ax, e1y = by - ay, e2x = cx - ax, e2y = cy - ay;
@@ -327,8 +332,8 @@ int orc_draw_triangles(const orc_config *cfg, const float *mesh_vertices, const 
     nth = omp_get_max_threads();
 #endif
     orc_fragbuf *fbs = (orc_fragbuf *)calloc((size_t)nth, sizeof(orc_fragbuf));
-    int64_t skipped = 0, dropped = 0;
-#pragma omp parallel reduction(+ : skipped, dropped)
+    int64_t skipped = 0, dropped = 0, overcap = 0;
+#pragma omp parallel reduction(+ : skipped, dropped, overcap)
     {
         int tid = 0;
 #ifdef _OPENMP
@@ -336,9 +341,9 @@ int orc_draw_triangles(const orc_config *cfg, const float *mesh_vertices, const 
 #endif
 #pragma omp for schedule(dynamic, 256)
         for (int64_t p = 0; p < nprim; ++p)
-            orc_raster_one(prims + 3 * (size_t)st * p, st, W, H, prim_id[p], &fbs[tid], &skipped, &dropped);
+            orc_raster_one(prims + 3 * (size_t)st * p, st, W, H, prim_id[p], &fbs[tid], &skipped, &dropped, &overcap);
     }
-    S.skipped_z0 = skipped; S.dropped_large = dropped;
+    S.skipped_z0 = skipped; S.dropped_large = dropped; S.over_capacity = overcap;
     for (int t = 0; t < nth; ++t) S.fragments += fbs[t].n;
 
     /* 5. DepthTest (:434, kernel :80-93) */

@@ -158,9 +158,15 @@ def bench_raycast(args, rank, world):
     rc = Raycaster([ren.Mesh(vb, None)])
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
-    targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]     # F x 33 MB > L2
-    local = torch.empty((F, RAY_H, RAY_W), dtype=torch.int32, device="cuda")
-    gathered = torch.empty((n_frames, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
+    store = parallel.FrameStore(n_frames, RAY_W, RAY_H) if (world > 1 and args.gather == "peer") else None
+    fused = store is not None and store.ok
+    if fused:   # render targets ARE rank 0's frame store (peer-mapped): the kernel's BGRA8 stores are the gather
+        targets = [ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(k)) for k in my_frames]
+        local = gathered = None
+    else:
+        targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]     # F x 33 MB > L2
+        local = torch.empty((F, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if world > 1 else None
+        gathered = torch.empty((n_frames, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
     cams = {k: ray_camera(ren, k) for k in range(n_frames * (args.steps + args.warmup))}
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * args.steps)]
 
@@ -171,7 +177,12 @@ def bench_raycast(args, rank, world):
             rc.render(targets[j], cams[s * n_frames + k])
             if timed_idx is not None:
                 ev[timed_idx * F + j][1].record()
-        if world > 1:   # the only collective: finished frames -> rank 0
+        collect()
+
+    def collect():   # the only collective: finished frames -> rank 0
+        if fused:
+            store.commit()
+        elif world > 1:
             for j in range(F):
                 local[j].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W))
             parallel.gather_frames(local, gathered, n_frames)
@@ -206,19 +217,19 @@ def bench_raycast(args, rank, world):
     from rendertoy_b200 import scenes
     from rendering._raycaster import camera_frame
 
+    # e2e delivers frames to HOST memory: on one node every rank reads its own frames back over its own PCIe link, so
+    # the GPU-side gather to rank 0 is not on this path (local targets, no collective)
+    e2e_targets = targets if not fused else [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
+
     def e2e_step(s):
         for j, k in enumerate(my_frames):
             world_m, view, proj = scenes.lesson_camera(ren, 6, orbit_t(s * n_frames + k), RAY_W, RAY_H)   # host inputs
             cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world_m, dtype=ren.float4x4))
-            rc.render(targets[j], cam)
+            rc.render(e2e_targets[j], cam)
             done[j % 2].record()
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[j % 2])
-                host[j % 2].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W), non_blocking=True)
-        if world > 1:
-            for j in range(F):
-                local[j].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W))
-            parallel.gather_frames(local, gathered, n_frames)
+                host[j % 2].copy_(e2e_targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W), non_blocking=True)
         torch.cuda.current_stream().wait_stream(copy_stream)
 
     e2e_step(0)
@@ -245,7 +256,10 @@ def bench_raycast(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[3]: dragon100k (synthetic stand-in for the missing dragon.obj, 100000 triangles) "
                                "raycast 3840x2160, lesson06 camera orbit, primary rays + closest hit + Lambert shade",
-                   "frames_per_rank_per_step": F, "partition": "frames k = rank (mod N), framebuffers gathered to rank 0 (NCCL)",
+                   "frames_per_rank_per_step": F,
+                   "partition": "frames k = rank (mod N); " + ("every rank's kernel stores its pixels straight into rank 0's frame store "
+                                "over NVLink (CUDA IPC peer memory), one barrier per step" if fused else
+                                "framebuffers gathered to rank 0 with NCCL send/recv" if world > 1 else "single GPU, no gather"),
                    "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
                          "L2-resident by design, as they are reused every frame",
                    "bvh_build_excluded": True},
@@ -261,7 +275,7 @@ def bench_raycast(args, rank, world):
                                             "FMA as 2 flop, this kernel is compiled -fmad=false for bit-exact parity"}},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": 4 * RAY_W * RAY_H * F,
                 "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async D2H of the "
-                                        "33 MB BGRA8 frame into pinned memory (PCIe-bound)"},
+                                        "33 MB BGRA8 frame into pinned memory (PCIe-bound); every rank reads back its own frames"},
         "gpu_launches": F * args.steps, "clocks": clocks,
     }
     return out, rows
@@ -285,12 +299,15 @@ def bench_raster(args, rank, world, rows=None):
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
     # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
+    store = parallel.FrameStore(n_frames, RAS_W, RAS_H) if (world > 1 and args.gather == "peer") else None
+    fused = store is not None and store.ok
     rasters = []
-    for _ in range(F):
-        pres = ren.create_presenter(RAS_W, RAS_H)
-        rasters.append(lessons.build_lesson08(ren, pres.get_render_target()))
-    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda")
-    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
+    for j in range(F):
+        target = ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(my_frames[j])) if fused else \
+            ren.create_presenter(RAS_W, RAS_H).get_render_target()
+        rasters.append(lessons.build_lesson08(ren, target))
+    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (world > 1 and not fused) else None
+    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1 and not fused) else None
     cams = {k: scenes.lesson_camera(ren, 8, orbit_t(k), RAS_W, RAS_H) for k in range(n_frames * (args.steps + args.warmup + 6))}
 
     def frame(j, k):
@@ -299,7 +316,9 @@ def bench_raster(args, rank, world, rows=None):
         lessons.render_frame(ren, raster, vb)
 
     def gather():
-        if world > 1:
+        if fused:
+            store.commit()
+        elif world > 1:
             for j in range(F):
                 local[j].copy_(rasters[j][0].get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W))
             parallel.gather_frames(local, gathered, n_frames)
@@ -327,9 +346,12 @@ def bench_raster(args, rank, world, rows=None):
     copy_stream = torch.cuda.Stream()
     done = [torch.cuda.Event() for _ in range(2)]
 
+    e2e_rasters = rasters if not fused else [lessons.build_lesson08(ren, ren.create_presenter(RAS_W, RAS_H).get_render_target())
+                                             for _ in range(F)]
+
     def e2e_step(s):
         for j, k in enumerate(my_frames):
-            raster, g = rasters[j]
+            raster, g = e2e_rasters[j]
             cam = scenes.lesson_camera(ren, 8, orbit_t(s * n_frames + k), RAS_W, RAS_H)      # host matrices every frame
             lessons.set_transforms(ren, g, *cam)
             lessons.render_frame(ren, raster, vb)
@@ -337,7 +359,6 @@ def bench_raster(args, rank, world, rows=None):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[j % 2])
                 host[j % 2].copy_(raster.get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W), non_blocking=True)
-        gather()
         torch.cuda.current_stream().wait_stream(copy_stream)
 
     e2e_step(args.steps + args.warmup)
@@ -456,6 +477,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="raycast", choices=["raycast", "raster"], help="which half of the metric is the primary line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = kernels write into rank 0's IPC-mapped frame store (fused); nccl = send/recv gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

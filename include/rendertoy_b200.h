@@ -122,6 +122,16 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
                        int64_t bgra_pitch_px, void *d_ctl, void *d_stats, void *stream);
 
+/* ---- multi-GPU frame store  (no reference counterpart: rendering/_core.py:10-11 is single-device) -------
+ * Rank 0 allocates the store (cudaMalloc, IPC-exportable) and exports a 64-byte handle; the other ranks of the
+ * node open it and pass addresses inside it as `d_bgra` to rt_raycast_primary / rt_raster_draw_triangles /
+ * rt_raster_clear_color, so finished pixels land in rank 0's HBM over NVLink from inside the shading kernel. */
+int rt_peer_alloc(int64_t bytes, void **out_d_ptr);
+int rt_peer_free(void *d_ptr);
+int rt_peer_export(const void *d_ptr, void *handle64);
+int rt_peer_open(const void *handle64, void **out_d_ptr);
+int rt_peer_close(void *d_ptr);
+
 #ifdef __cplusplus
 }
 #endif

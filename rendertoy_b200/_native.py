@@ -34,6 +34,11 @@ SIGNATURES = {
     "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
                                      _I64, _VP, _VP, _VP]),
+    "rt_peer_alloc": (C.c_int, [_I64, C.POINTER(_VP)]),
+    "rt_peer_free": (C.c_int, [_VP]),
+    "rt_peer_export": (C.c_int, [_VP, _VP]),
+    "rt_peer_open": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "rt_peer_close": (C.c_int, [_VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),
     "rt_texture_destroy": (C.c_int, [_U64]),
 }

@@ -1,0 +1,50 @@
+// rt_peer.cu -- peer-memory plumbing for the multi-GPU framebuffer gather (the reference
+// is single-device, rendering/_core.py:10-11).
+//
+// Rank 0 owns one cudaMalloc'ed frame store and exports it with CUDA IPC; every other rank maps it and hands the
+// mapped address to rt_raycast_primary / rt_raster_draw_triangles as the render target.  The shading kernels then
+// store their BGRA8 pixels straight into rank 0's HBM over NVLink while they are still tracing: the "gather" is
+// fused into the producing kernel and the only thing left of the collective is a barrier.
+#include "rt_common.cuh"
+
+extern "C" {
+
+int rt_peer_alloc(int64_t bytes, void **out_d_ptr)
+{
+    RT_REQUIRE(bytes > 0 && out_d_ptr, "size / out pointer");
+    RT_CUDA(cudaMalloc(out_d_ptr, (size_t)bytes));
+    return RT_OK;
+}
+
+int rt_peer_free(void *d_ptr)
+{
+    if (d_ptr) RT_CUDA(cudaFree(d_ptr));
+    return RT_OK;
+}
+
+int rt_peer_export(const void *d_ptr, void *handle64)
+{
+    RT_REQUIRE(d_ptr && handle64, "pointer / handle buffer (64 bytes)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    RT_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle64, &h, 64);
+    return RT_OK;
+}
+
+int rt_peer_open(const void *handle64, void **out_d_ptr)
+{
+    RT_REQUIRE(handle64 && out_d_ptr, "handle / out pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    RT_CUDA(cudaIpcOpenMemHandle(out_d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+
+int rt_peer_close(void *d_ptr)
+{
+    if (d_ptr) RT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RT_OK;
+}
+
+} // extern "C"

@@ -465,20 +465,13 @@ __device__ __noinline__ bool find_source_cell(const PrimRec &p, const Edges &e, 
     return false;
 }
 
+// Shade one pixel whose key names a winner of this draw.
 template <int SHADER>
-__global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs a)
+__device__ __forceinline__ void resolve_pixel(const ResolveArgs &a, int x, int y, unsigned long long k64)
 {
-    // 256 threads cover a 32x8 pixel block; each warp an 8x4 tile, so its lanes share few primitives
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->n_items = 0; // queue drained: re-arm for the next draw
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7), y = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
-    if (x >= a.width || y >= a.height) return;
     const size_t p = (size_t)y * a.width + x;
-    const unsigned long long k64 = a.key[p];
     const unsigned prim = (unsigned)k64;
-    if (prim == RT_NO_PRIMITIVE) return;
     const uint32_t zbits = (uint32_t)(k64 >> 32);
-
     const float4 *r = a.rec + (size_t)prim * RecLayout<SHADER>::F4;
     PrimRec pr;
     pr.h1 = __ldg(r); pr.h2 = __ldg(r + 1); pr.h3 = __ldg(r + 2);
@@ -515,6 +508,29 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs a)
     const float z = __uint_as_float(zbits);
     if (!(z <= 0)) a.bgra[p] = rt_pack_bgra(color.x, color.y, color.z, color.w); // FragmentProcess, :102
     a.key[p] = k64 | 0xFFFFFFFFull; // re-arm: later draws win depth ties, as in the reference's draw order
+}
+
+// 256 threads cover a 32x32 pixel block; each warp an 8x16 strip of which every lane owns 4 pixels (rows y, y+4,
+// y+8, y+12).  The four key loads are issued before any is used: the kernel is bound by the latency of that one
+// dependent load per pixel, so memory-level parallelism is what buys time here.
+template <int SHADER>
+__global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->n_items = 0; // queue drained: re-arm for the next draw
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7), y0 = blockIdx.y * 32 + (wid >> 2) * 16 + (lane >> 3);
+    if (x >= a.width) return;
+    unsigned long long k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int y = y0 + 4 * i;
+        k[i] = y < a.height ? __ldcs(a.key + (size_t)y * a.width + x) : ~0ull;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const unsigned long long k64 = i == 0 ? k[0] : i == 1 ? k[1] : i == 2 ? k[2] : k[3];
+        if ((unsigned)k64 != RT_NO_PRIMITIVE) resolve_pixel<SHADER>(a, x, y0 + 4 * i, k64);
+    }
 }
 
 // ---- clears and depth views -----------------------------------------------------------------------
@@ -580,7 +596,7 @@ int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scr
             RT_CUDA(cudaGetLastError());
         }
     }
-    dim3 grid((ra.width + 31) / 32, (ra.height + 7) / 8), block(256);
+    dim3 grid((ra.width + 31) / 32, (ra.height + 31) / 32), block(256);
     resolve_kernel<SHADER><<<grid, block, 0, st>>>(ra);
     RT_CUDA(cudaGetLastError());
     return RT_OK;

@@ -79,3 +79,79 @@ def gather_frames(local_frames: torch.Tensor, all_frames: torch.Tensor, n_frames
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+class _RawDeviceMemory:
+    """Adapter exposing a raw device address to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+class FrameStore:
+    """n_frames BGRA8 frames of W x H in rank `dst`'s HBM, writable from every rank of the node.
+
+    The fused alternative to gather_frames(): rank `dst` cudaMalloc's the store and exports it with CUDA IPC, the
+    other ranks map it, and `frame(k)` returns a torch uint8 view a render target can be built on
+    (`rendering.Image(W, H, RGBA, memory=store.frame(k))`).  The ray-cast / resolve kernels then write finished
+    pixels straight into rank dst's memory over NVLink while they run; `commit()` (a barrier) is all that remains of
+    the collective.  Falls back (ok=False) when IPC mapping is unavailable; callers then use gather_frames()."""
+
+    def __init__(self, n_frames, width, height, dst=0):
+        import ctypes
+        from . import _native
+        self.n_frames, self.width, self.height, self.dst = n_frames, width, height, dst
+        self.frame_bytes = width * height * 4
+        self.rank = dist.get_rank() if _is_dist() else 0
+        self.world = dist.get_world_size() if _is_dist() else 1
+        self._native, self._base, self._owner = _native, None, self.rank == dst
+        nbytes = self.frame_bytes * n_frames
+        handle = [None]
+        ok = True
+        try:
+            if self._owner:
+                p = ctypes.c_void_p()
+                _native.call("rt_peer_alloc", nbytes, ctypes.byref(p))
+                self._base = p.value
+                buf = ctypes.create_string_buffer(64)
+                _native.call("rt_peer_export", self._base, buf)
+                handle = [bytes(buf.raw)]
+        except Exception:
+            ok = False
+        if self.world > 1:
+            dist.broadcast_object_list(handle, src=dst)
+            if not self._owner and handle[0] is not None:
+                try:
+                    p = ctypes.c_void_p()
+                    _native.call("rt_peer_open", ctypes.create_string_buffer(handle[0], 64), ctypes.byref(p))
+                    self._base = p.value
+                except Exception:
+                    ok = False
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok and self._base is not None)
+            ok = all(flags)
+        self.ok = ok and self._base is not None
+        self.memory = torch.as_tensor(_RawDeviceMemory(self._base, nbytes), device="cuda") if self.ok else None
+
+    def frame(self, k):
+        """uint8 view (frame_bytes,) of frame k."""
+        return self.memory[k * self.frame_bytes:(k + 1) * self.frame_bytes]
+
+    def frames(self):
+        """(n_frames, H, W) int32 view -- meaningful on rank `dst` after commit()."""
+        return self.memory.view(torch.int32).view(self.n_frames, self.height, self.width)
+
+    def commit(self):
+        """All ranks' kernels writing into the store have finished once every rank passes this barrier."""
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        if self._base is None:
+            return
+        self.memory = None
+        if self._owner:
+            self._native.call("rt_peer_free", self._base)
+        else:
+            self._native.call("rt_peer_close", self._base)
+        self._base = None

@@ -148,10 +148,14 @@ class _Storage:
     when to refresh; allocations <= 64 KiB keep a host shadow."""
     __slots__ = ("tensor", "nbytes", "host", "host_valid", "dev_valid", "version", "cache")
 
-    def __init__(self, nbytes, dev=None):
-        dev = dev or device()
+    def __init__(self, nbytes, dev=None, tensor=None):
         self.nbytes = int(nbytes)
-        self.tensor = torch.zeros(max(self.nbytes, 1), dtype=torch.uint8, device=dev)
+        if tensor is not None:      # adopt existing device memory (e.g. a slice of a peer-mapped frame store)
+            assert tensor.dtype == torch.uint8 and tensor.is_contiguous() and tensor.numel() >= self.nbytes
+            self.tensor = tensor
+        else:
+            dev = dev or device()
+            self.tensor = torch.zeros(max(self.nbytes, 1), dtype=torch.uint8, device=dev)
         self.host = np.zeros(self.nbytes, dtype=np.uint8) if self.nbytes <= _HOST_SHADOW_MAX else None
         self.host_valid = self.host is not None
         self.dev_valid = True
@@ -378,14 +382,17 @@ class Image:
     """2-D image in linear device memory, row-major, `components` channels per pixel.  For the RGBA dtype the
     bytes are B,G,R,A (CL_BGRA UNORM8) exactly as the reference's render target (rendering/_core.py:340)."""
 
-    def __init__(self, width, height, dtype):
+    def __init__(self, width, height, dtype, memory=None):
+        """memory: optional torch uint8 tensor (width*height*pixel bytes) to use instead of a fresh allocation --
+        e.g. one frame of a parallel.FrameStore, which may live on another GPU of the node."""
         dtype = np.dtype(dtype) if not isinstance(dtype, np.dtype) else dtype
         assert dtype in _IMAGE_FORMATS, "Unsupported dtype for image format"
         self.width, self.height, self.depth = int(width), int(height), 0
         self.dtype = dtype
         self.components, self.channel_dtype, self.is_bgra8 = _IMAGE_FORMATS[dtype]
         item = np.dtype(self.channel_dtype).itemsize * self.components
-        self.buffer = DeviceBuffer(_Storage(self.width * self.height * item), 0, (self.height, self.width, self.components),
+        nbytes = self.width * self.height * item
+        self.buffer = DeviceBuffer(_Storage(nbytes, tensor=memory), 0, (self.height, self.width, self.components),
                                    np.dtype(self.channel_dtype))
 
     @property

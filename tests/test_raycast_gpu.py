@@ -51,6 +51,31 @@ def test_primary_rays_match_bruteforce(ren, oracle, n_tris, w, h, lesson):
     assert np.array_equal(target.get(), shaded), "Lambert BGRA8 differs from the oracle"
 
 
+def test_textured_shading_matches_oracle(ren, oracle):
+    """configs[2]: lesson09-style shading of ray-cast hits (texture over P.xy*2, L = 0.2 + max(0, N.l))."""
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200._native import SHADER_LESSON09
+    rows = scenes.dragon(3_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    w, h = 160, 120
+    cam = _camera(ren, 8, 1.3, w, h)
+    rgb = np.random.default_rng(3).integers(0, 256, size=(31, 45, 3), dtype=np.uint8)
+    mem, desc = ren.create_texture2D(45, 31)
+    with ren.mapped(mem) as m:
+        m = m.view(np.float32).ravel().reshape(31, 45, 4)
+        m[:, :, 0:3] = rgb / 255.0
+        m[:, :, 3] = 1.0
+        texf = np.array(m)
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    hits = torch.empty((w * h, 4), dtype=torch.float32, device="cuda")
+    rc.render(target, cam, shader=SHADER_LESSON09, texture_descriptor=desc, hits=hits)
+    ref = oracle.raycast_brute(rows, oracle.primary_rays(cam, w, h))
+    _check(hits.cpu().numpy(), ref, "textured")
+    shaded = oracle.shade_hits(9, rows, ref[1], ref[2], ref[3], texture=texf).reshape(h, w, 4)
+    assert (ref[1] != 0xFFFFFFFF).sum() > 2000
+    assert np.array_equal(target.get(), shaded), "textured BGRA8 differs from the oracle"
+
+
 def test_ray_buffer_matches_bruteforce(ren, oracle):
     from rendering._raycaster import Raycaster, Ray
     rows = scenes.dragon(1_500)

@@ -171,14 +171,14 @@ __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, 
 //     whatever the mix of sizes.  A cell finds its primitive with one warp OR-reduce + popc: owners flag the
 //     cell where their primitive starts, and a cell's slot is the number of starts at or before it;
 //   * primitives with a large bbox are NOT walked here -- one warp stuck on a few thousand cells would be the
-//     kernel's critical path.  They are cut into CHUNK-cell work items appended to a global queue
+//     kernel's critical path.  They are cut into work items of 32 row-quads appended to a global queue
 //     (one warp-aggregated atomicAdd) that coverage_kernel drains with every warp of the machine.
 // Candidate cells (those the division-free sign test cannot reject) are compacted through a per-warp
 // shared-memory ring, so the exact test + depth atomics always run with full warps.
 
 constexpr int RW = 4;           // warps per raster block
 constexpr int SMALL_MAX = 64;   // largest bbox (cells) rasterized inline by the owning warp
-constexpr int CHUNK = 128;      // cells per queued work item of a large primitive
+constexpr int QUADS = 32;       // a queued work item = 32 row-quads (4 cells along x each) of a large primitive
 constexpr int RING = 64;        // per-warp candidate ring (entries)
 
 struct __align__(16) Slot { // 24 words, read as six 128-bit loads (the last two only for candidate cells)
@@ -248,6 +248,7 @@ __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3
     s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
     s.h3x = p3.x; s.h3y = p3.y; s.h3z = p3.z;
     s.pad = 0.0f;
+    s.off = bb.ny; // large primitives keep ny here; the inline path overwrites it with the cell offset
     return bb.nx * bb.ny;
 }
 
@@ -290,7 +291,7 @@ __device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned p
 }
 
 template <int SHADER>
-__global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, const unsigned capacity)
+__global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
 {
     __shared__ Slot slots[RW][32];
     __shared__ unsigned ring[RW][RING];
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
         // large primitives -> global work queue (falls back to inline if the queue is full)
         const unsigned big = __ballot_sync(FULL, ncells > SMALL_MAX);
         if (big) {
-            const int nchunks = ncells > SMALL_MAX ? (ncells + CHUNK - 1) / CHUNK : 0;
+            // work items count row-quads: ceil(nx/4) * ny quads, QUADS per item
+            const int nchunks = ncells > SMALL_MAX ? ((((mine.nx_tle & 0xffff) + 3) >> 2) * mine.off + QUADS - 1) / QUADS : 0;
             int incl = nchunks;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -329,8 +331,11 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
             base = __shfl_sync(FULL, base, 0);
             if (base + (unsigned)tot <= capacity) {
                 unsigned w = base + (unsigned)(incl - nchunks);
-                for (int j = 0; j < nchunks; ++j) items[w + j] = make_uint2(mine.prim, (unsigned)j);
-                if (nchunks) ncells = 0; // handed over
+                if (nchunks) {
+                    bigslots[w] = mine; // setup travels with the first item: coverage_kernel recomputes nothing
+                    for (int j = 0; j < nchunks; ++j) items[w + j] = make_uint2(w, (unsigned)j);
+                    ncells = 0; // handed over
+                }
             } else if (lane == 0) {
                 atomicSub(&ctl->n_items, (unsigned)tot); // give the reservation back; rasterize inline below
                 atomicAdd(&ctl->overflowed, 1u);
@@ -392,39 +397,66 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
 }
 
 // ---- kernel 1b: coverage of the queued large primitives ---------------------------------------------
-// Persistent grid; each warp takes whole work items (primitive, chunk) round-robin.  A lane owns CHUNK/32
-// cells of the item: it first runs the sign test on all of them, then the exact test only on survivors.
+// Persistent grid; each warp takes whole work items round-robin.  An item is 32 row-quads of one primitive: a
+// lane owns 4 horizontally adjacent cells, so the row term b*py of each edge function is shared (bit-identical:
+// the reference evaluates a*px + b*py + c as (a*px + b*py) + c, and fl(b*py) does not depend on px).  Lanes
+// sign-test their 4 cells; the survivors of the whole warp are then dealt out one per lane (ballot + find-nth-set)
+// so the exact test -- 3 IEEE divisions, depth, 64-bit atomicMin -- always runs on full warps.
 template <int SHADER>
-__global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items)
+__global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items, const Slot *bigslots)
 {
+    const unsigned FULL = 0xffffffffu;
     const unsigned n_items = ctl->n_items;
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int W = a.width, H = a.height;
     for (unsigned i = warp; i < n_items; i += n_warps) {
         const uint2 it = items[i];
-        const float4 *r = a.rec + (size_t)it.x * RecLayout<SHADER>::F4;
-        const float4 h1 = __ldcg(r), h2 = __ldcg(r + 1), h3 = __ldcg(r + 2); // written by raster_kernel: bypass L1
-        const BBox bb = bbox_setup(h1.x, h1.y, h2.x, h2.y, h3.x, h3.y, W, H);
-        const Edges e = edge_setup(h1.x, h1.y, h2.x, h2.y, h3.x, h3.y);
-        const int ncells = bb.nx * bb.ny, first = (int)it.y * CHUNK;
-        const float inv_nx = 1.0f / (float)bb.nx;
-        unsigned cand = 0;
-        const int nj = (min(ncells - first, CHUNK) + 31) >> 5; // warp-uniform
-        for (int j = 0; j < nj; ++j) {
-            const int local = first + j * 32 + lane;
-            if (local < ncells) {
-                const int rr = (int)(((float)local + 0.5f) * inv_nx);
-                if (cell_maybe_inside(e, bb.startx + (local - rr * bb.nx), bb.starty + rr)) cand |= 1u << j;
+        const float4 *sp = reinterpret_cast<const float4 *>(bigslots + it.x);
+        const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3), s4 = __ldcg(sp + 4), s5 = __ldcg(sp + 5);
+        Edges e;
+        e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
+        e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x;
+        const int ny = __float_as_int(s2.z), sxy = __float_as_int(s2.w), nx_tle = __float_as_int(s3.x);
+        e.tle = (unsigned)(nx_tle >> 16);
+        const int nx = nx_tle & 0xffff, startx = sxy & 0xffff, starty = sxy >> 16;
+        const int nxq = (nx + 3) >> 2, nquads = nxq * ny;
+        const unsigned prim = __float_as_uint(s3.y);
+
+        const int q = (int)it.y * QUADS + lane;
+        unsigned cand = 0; // bit c: cell (col0 + c, row) survives the sign test
+        int col0 = 0, row = 0;
+        if (q < nquads) {
+            const int r = (int)(((float)q + 0.5f) * __frcp_rn((float)nxq)); // exact: q, nxq < 4096
+            col0 = startx + 4 * (q - r * nxq);
+            row = starty + r;
+            const float py = (float)row + 0.5f;
+            const float t1 = e.b1 * py, t2 = e.b2 * py, t3 = e.b3 * py;
+            const int ncol = min(4, startx + nx - col0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float px = (float)(col0 + c) + 0.5f;
+                const float d1 = e.a1 * px + t1 + e.c1, d2 = e.a2 * px + t2 + e.c2, d3 = e.a3 * px + t3 + e.c3;
+                const float s = d1 + d2 + d3;
+                if (c < ncol && !(d1 * s < 0.0f || d2 * s < 0.0f || d3 * s < 0.0f)) cand |= 1u << c;
             }
         }
-        while (cand) {
-            const int j = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const int local = first + j * 32 + lane;
-            const int rr = (int)(((float)local + 0.5f) * inv_nx);
-            cover_cell(e, bb.startx + (local - rr * bb.nx), bb.starty + rr, h1.x, h1.y, h1.z, h2.x, h2.y, h2.z, h3.x, h3.y, h3.z,
-                       it.x, a.key, W, H);
+        // deal the warp's candidates out, 32 per round
+        const unsigned m0 = __ballot_sync(FULL, cand & 1u), m1 = __ballot_sync(FULL, cand & 2u), m2 = __ballot_sync(FULL, cand & 4u),
+                       m3 = __ballot_sync(FULL, cand & 8u);
+        const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), total = c2 + __popc(m3);
+        for (int base = 0; base < total; base += 32) {
+            const int k = base + lane;
+            const bool act = k < total;
+            int c = 0, src = 0;
+            if (act) {
+                c = k < c0 ? 0 : k < c1 ? 1 : k < c2 ? 2 : 3;
+                const unsigned m = c == 0 ? m0 : c == 1 ? m1 : c == 2 ? m2 : m3;
+                const int before = c == 0 ? 0 : c == 1 ? c0 : c == 2 ? c1 : c2;
+                src = (int)__fns(m, 0, k - before + 1); // lane that owns this candidate
+            }
+            const int scol = __shfl_sync(FULL, col0, src), srow = __shfl_sync(FULL, row, src);
+            if (act) cover_cell(e, scol + c, srow, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, prim, a.key, W, H);
         }
     }
 }
@@ -577,22 +609,23 @@ constexpr size_t CTL_BYTES = 256;
 template <int SHADER>
 int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scratch_bytes, cudaStream_t st)
 {
-    // scratch = [WorkCtl, 256 B][records: 2 per triangle][work items: whatever is left]
+    // scratch = [WorkCtl, 256 B][records: 2 per triangle][big-primitive slots: cap x 96 B][work items: cap x 8 B]
     char *base = (char *)scratch;
     WorkCtl *ctl = (WorkCtl *)base;
     const long long rec_bytes = 2 * da.n_tris * RecLayout<SHADER>::F4 * 16;
-    uint2 *items = (uint2 *)(base + CTL_BYTES + rec_bytes);
-    long long cap = (scratch_bytes - (long long)CTL_BYTES - rec_bytes) / (long long)sizeof(uint2);
+    long long cap = (scratch_bytes - (long long)CTL_BYTES - rec_bytes) / (long long)(sizeof(uint2) + sizeof(Slot));
     if (cap < 0) cap = 0;
     if (cap > 0x7fffffffll) cap = 0x7fffffffll;
+    Slot *bigslots = (Slot *)(base + CTL_BYTES + rec_bytes);
+    uint2 *items = (uint2 *)(base + CTL_BYTES + rec_bytes + cap * (long long)sizeof(Slot));
     ra.ctl = ctl;
     if (da.n_tris > 0) {
         // one warp per 32 triangles, RW warps per block; the hardware block scheduler does the load balancing
         long long blocks = (da.n_tris + RW * 32 - 1) / (RW * 32);
-        raster_kernel<SHADER><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, (unsigned)cap);
+        raster_kernel<SHADER><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
         RT_CUDA(cudaGetLastError());
         if (cap > 0) {
-            coverage_kernel<SHADER><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items);
+            coverage_kernel<SHADER><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
             RT_CUDA(cudaGetLastError());
         }
     }
@@ -664,11 +697,12 @@ int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int 
 {
     const int64_t f4 = shader == RT_SHADER_LESSON08 ? 4 : 6;
     const int64_t rec = 2 * n_triangles * f4 * 16; // up to two primitives per input triangle
-    // work items: one per CHUNK cells of a large primitive.  The reference caps one pass at 32*W*H bbox cells
-    // (_raster.py:378); sized for that plus one partial chunk per primitive, bounded so huge meshes of tiny
-    // triangles do not pay for a queue they never use.  A full queue only means inline (slower) coverage.
-    int64_t items = 32ll * width * height / CHUNK + (2 * n_triangles < (1ll << 22) ? 2 * n_triangles : (1ll << 22));
-    return (int64_t)CTL_BYTES + rec + items * (int64_t)sizeof(uint2);
+    // work items: one per 32 row-quads (<= 128 cells) of a large primitive, each with room for a 96 B setup slot.
+    // The reference caps one pass at 32*W*H bbox cells (_raster.py:378); sized for a quarter of that plus one
+    // partial item per primitive, bounded to 2^21 items (208 MB).  A full queue only means inline (slower) coverage.
+    int64_t items = 8ll * width * height / (4 * QUADS) + (2 * n_triangles < (1ll << 20) ? 2 * n_triangles : (1ll << 20));
+    if (items > (1ll << 21)) items = 1ll << 21;
+    return (int64_t)CTL_BYTES + rec + items * (int64_t)(sizeof(uint2) + sizeof(Slot));
 }
 
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles, int shader,

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librendertoy_b200.so")
+LIB_PATH = os.environ.get("RENDERTOY_B200_LIB") or os.path.join(HERE, "librendertoy_b200.so")   # override: A/B builds
 
 SHADER_LESSON08 = 8
 SHADER_LESSON09 = 9

@@ -177,15 +177,15 @@ __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, 
 // shared-memory ring, so the exact test + depth atomics always run with full warps.
 
 constexpr int RW = 4;           // warps per raster block
-constexpr int SMALL_MAX = 64;   // largest bbox (cells) rasterized inline by the owning warp
+constexpr int SMALL_MAX = 256;  // largest bbox (cells) rasterized inline by the owning warp
 constexpr int QUADS = 32;       // a queued work item = 32 row-quads (4 cells along x each) of a large primitive
-constexpr int RING = 64;        // per-warp candidate ring (entries)
+constexpr int RING = 160;       // per-warp candidate stack: < 32 left over + up to 4 new per lane per pass
 
 struct __align__(16) Slot { // 24 words, read as six 128-bit loads (the last two only for candidate cells)
     float a1, b1, c1, a2;
     float b2, c2, a3, b3;
     float c3, inv_nx; int off; int sxy;        // sxy = startx | starty << 16
-    int nx_tle; unsigned prim; float h1x, h1y; // nx_tle = nx | tle << 16
+    int nx_tle; unsigned prim; float h1x, h1y; // nx_tle = nx | tle << 16 | robust << 19 | (s < 0) << 20
     float h1z, h2x, h2y, h2z;
     float h3x, h3y, h3z, pad;
 };
@@ -215,6 +215,32 @@ __device__ __forceinline__ void cover_cell(const Edges &e, int col, int row, flo
     atomicMin(key + (size_t)iy * W + ix, k64);
 }
 
+// Row spans need sign(s) to be one constant over the whole bbox (s = d1 + d2 + d3, twice the signed area up to
+// rounding).  In real arithmetic s is affine in (px, py), so it lies between its four corner values; the float
+// evaluation differs from it by less than N/2 with N = 2^-20 * sum of term magnitudes (a generous 16 ulp).  Hence if
+// all four corner values exceed N with one sign, every cell's float s has that sign and is non-zero.  Returns
+// 0 (not robust: slivers, NaN/inf), +1 or -1.
+__device__ __forceinline__ int robust_sign(const Edges &e, const BBox &bb)
+{
+    const float x0 = (float)bb.startx + 0.5f, x1 = (float)(bb.startx + bb.nx - 1) + 0.5f;
+    const float y0 = (float)bb.starty + 0.5f, y1 = (float)(bb.starty + bb.ny - 1) + 0.5f;
+    const float n = 9.5367431640625e-7f * ((fabsf(e.a1) + fabsf(e.a2) + fabsf(e.a3)) * x1 + (fabsf(e.b1) + fabsf(e.b2) + fabsf(e.b3)) * y1 +
+                                           (fabsf(e.c1) + fabsf(e.c2) + fabsf(e.c3)));
+    float smin = INFINITY, smax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float px = (c & 1) ? x1 : x0, py = (c & 2) ? y1 : y0;
+        const float d1 = e.a1 * px + e.b1 * py + e.c1, d2 = e.a2 * px + e.b2 * py + e.c2, d3 = e.a3 * px + e.b3 * py + e.c3;
+        const float sv = d1 + d2 + d3;
+        smin = fminf(smin, sv); smax = fmaxf(smax, sv);
+        if (!(sv == sv)) return 0;
+    }
+    if (!(n > 1e-18f) || !(n < INFINITY)) return 0;
+    if (smin > n) return 1;
+    if (smax < -n) return -1;
+    return 0;
+}
+
 template <int SHADER>
 __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3, unsigned prim, Slot &s)
 {
@@ -242,7 +268,8 @@ __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3
     s.a3 = e.a3; s.b3 = e.b3; s.c3 = e.c3;
     s.inv_nx = 1.0f / (float)bb.nx;
     s.sxy = bb.startx | (bb.starty << 16);
-    s.nx_tle = bb.nx | ((int)e.tle << 16);
+    const int rs = robust_sign(e, bb);
+    s.nx_tle = bb.nx | ((int)e.tle << 16) | (rs != 0 ? 1 << 19 : 0) | (rs < 0 ? 1 << 20 : 0); // nx | tle<<16 | robust<<19 | s<0 <<20
     s.prim = prim;
     s.h1x = p1.x; s.h1y = p1.y; s.h1z = p1.z;
     s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
@@ -286,7 +313,7 @@ __device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned p
     const int col = (sxy & 0xffff) + (int)(packed & 0xfffu), row = (sxy >> 16) + (int)((packed >> 12) & 0xfffu);
     Edges e;
     e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
-    e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = (unsigned)(nx_tle >> 16);
+    e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = (unsigned)(nx_tle >> 16) & 7u;
     cover_cell(e, col, row, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, __float_as_uint(s3.y), key, W, H);
 }
 
@@ -342,53 +369,90 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
             }
         }
 
-        const unsigned nonempty = __ballot_sync(FULL, ncells > 0);
-        if (nonempty == 0) continue;
-        int incl = ncells; // inclusive warp scan of cell counts
+        // ---- inline coverage by row spans ---------------------------------------------------------------------
+        // The rows of the warp's staged primitives are laid end to end and taken 32 at a time, one row per lane.
+        // A lane finds the exact interval of its row that the division-free sign test accepts (the float edge
+        // functions are monotone in px, so per edge the accepted cells are a half-line: an analytic guess is
+        // corrected by evaluating the real predicate), pushes those cells on the warp's candidate stack, and
+        // full warps of candidates go through the exact test + depth atomics.
+        const int ny = ncells > 0 ? mine.off : 0; // setup_prim left ny in .off
+        const unsigned staged = __ballot_sync(FULL, ny > 0);
+        if (staged == 0) continue;
+        int incl = ny; // inclusive warp scan of row counts
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int v = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) incl += v;
         }
-        const int off = incl - ncells, total = __shfl_sync(FULL, incl, 31);
+        const int off = incl - ny, total = __shfl_sync(FULL, incl, 31);
         __syncwarp(); // previous pass finished reading the slots
-        if (ncells > 0) {
+        if (ny > 0) {
             mine.off = off;
-            my_slots[__popc(nonempty & lt_mask)] = mine;
+            my_slots[__popc(staged & lt_mask)] = mine;
         }
         __syncwarp();
 
-        int started = 0; // compacted primitives whose first cell lies before `base`
-        int pending = 0; // ring entries waiting for the exact test (warp-uniform)
+        int started = 0; // compacted primitives whose first row lies before `base`
+        int pending = 0; // candidates on the stack (warp-uniform, < 32 between passes)
         for (int base = 0; base < total; base += 32) {
             const unsigned rel = (unsigned)(off - base);
-            const unsigned starts = __reduce_or_sync(FULL, (ncells > 0 && rel < 32u) ? (1u << rel) : 0u);
+            const unsigned starts = __reduce_or_sync(FULL, (ny > 0 && rel < 32u) ? (1u << rel) : 0u);
             const int slot = started + __popc(starts & le_mask) - 1;
             started += __popc(starts);
-            const int c = base + lane;
-            bool cand = false;
-            unsigned packed = 0;
-            if (c < total) {
+            int lo = 0, hi = -1, lrow = 0;
+            if (base + lane < total) {
                 const float4 *sp = reinterpret_cast<const float4 *>(my_slots + slot);
                 const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
-                const int nx_tle = __float_as_int(sp[3].x);
-                const int local = c - __float_as_int(s2.z), sxy = __float_as_int(s2.w);
-                const int nx = nx_tle & 0xffff;
-                const int r = (int)(((float)local + 0.5f) * s2.y); // exact: local, nx < 4096
-                const int cl = local - r * nx;
-                Edges e;
-                e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
-                e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = 0;
-                cand = cell_maybe_inside(e, (sxy & 0xffff) + cl, (sxy >> 16) + r); // sign test, no division
-                packed = ((unsigned)slot << 24) | ((unsigned)r << 12) | (unsigned)cl;
+                const int nx_tle = __float_as_int(sp[3].x), sxy = __float_as_int(s2.w);
+                lrow = base + lane - __float_as_int(s2.z);
+                hi = (nx_tle & 0xffff) - 1;
+                if (nx_tle & (1 << 19)) { // sign(s) is one constant over the bbox: exact spans
+                    const float sg = (nx_tle & (1 << 20)) ? -1.0f : 1.0f;
+                    const float x0 = (float)(sxy & 0xffff) + 0.5f; // px of local column 0
+                    const float py = (float)((sxy >> 16) + lrow) + 0.5f;
+                    const float ea[3] = {s0.x, s0.w, s1.z}, eb[3] = {s0.y, s1.x, s1.w}, ec[3] = {s0.z, s1.y, s2.x};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float ak = ea[k], tk = eb[k] * py, ck = ec[k];
+                        // accepted(col) <=> !(sg * ((ak * px + tk) + ck) < 0), px = x0 + col  (same expression as cell_eval)
+                        const float dir = sg * ak;
+                        if (dir > 0.0f) {        // accepted for col >= L
+                            int L = __float2int_ru(__fdividef(-(tk + ck), ak) - x0);
+                            L = min(max(L, lo), hi + 1);
+                            while (L > lo && !(sg * ((ak * (x0 + (float)(L - 1)) + tk) + ck) < 0.0f)) --L;
+                            while (L <= hi && (sg * ((ak * (x0 + (float)L) + tk) + ck) < 0.0f)) ++L;
+                            lo = L;
+                        } else if (dir < 0.0f) { // accepted for col <= U
+                            int U = __float2int_rd(__fdividef(-(tk + ck), ak) - x0);
+                            U = min(max(U, lo - 1), hi);
+                            while (U < hi && !(sg * ((ak * (x0 + (float)(U + 1)) + tk) + ck) < 0.0f)) ++U;
+                            while (U >= lo && (sg * ((ak * (x0 + (float)U) + tk) + ck) < 0.0f)) --U;
+                            hi = U;
+                        } else if (sg * ((ak * x0 + tk) + ck) < 0.0f) { // constant along the row (ak == 0 or NaN): all or nothing
+                            hi = lo - 1;
+                        }
+                    }
+                }
             }
-            const unsigned cm = __ballot_sync(FULL, cand);
-            if (cand) my_ring[(pending + __popc(cm & lt_mask)) & (RING - 1)] = packed;
-            pending += __popc(cm);
-            __syncwarp();
-            if (pending >= 32) { // a full warp of candidates: exact test + atomics
-                pending -= 32;
-                cover_from_slot(my_slots, my_ring[(pending + lane) & (RING - 1)], a.key, W, H);
+            // push the spans, at most 4 cells per lane per pass, and drain full warps of candidates
+            int remaining = hi >= lo ? hi - lo + 1 : 0;
+            while (__any_sync(FULL, remaining > 0)) {
+                const int n = min(remaining, 4);
+                int pin = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(FULL, pin, d);
+                    if (lane >= d) pin += v;
+                }
+                const int ptot = __shfl_sync(FULL, pin, 31);
+                const unsigned head = ((unsigned)slot << 24) | ((unsigned)lrow << 12);
+                for (int j = 0; j < n; ++j) my_ring[pending + pin - n + j] = head | (unsigned)(lo + j);
+                lo += n; remaining -= n; pending += ptot;
+                __syncwarp();
+                while (pending >= 32) {
+                    pending -= 32;
+                    cover_from_slot(my_slots, my_ring[pending + lane], a.key, W, H);
+                }
                 __syncwarp();
             }
         }
@@ -418,7 +482,7 @@ __global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const W
         e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
         e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x;
         const int ny = __float_as_int(s2.z), sxy = __float_as_int(s2.w), nx_tle = __float_as_int(s3.x);
-        e.tle = (unsigned)(nx_tle >> 16);
+        e.tle = (unsigned)(nx_tle >> 16) & 7u;
         const int nx = nx_tle & 0xffff, startx = sxy & 0xffff, starty = sxy >> 16;
         const int nxq = (nx + 3) >> 2, nquads = nxq * ny;
         const unsigned prim = __float_as_uint(s3.y);

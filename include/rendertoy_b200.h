@@ -82,11 +82,15 @@ int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32
  *                    (the first 256 bytes are a control block the kernels keep at zero between draws);
  *                    holds the per-primitive setup records and the large-primitive work queue
  *   d_bgra           W*H*4 bytes, the render target
+ *   clear_rgba       NULL, or 4 floats: a clear(render_target, rgba) the caller deferred; folded into the resolve kernel
+ *                    (pixels no primitive wins are written with it) instead of a separate fill launch
+ *   clear_depth      non-zero: a deferred clear(depth_buffer, v) with v's bits in clear_depth_bits; executed first
  */
 int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int height);
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles,
                              int shader, const float *vs_globals, uint64_t tex_handle, int width, int height,
-                             void *d_key, void *d_scratch, int64_t scratch_bytes, void *d_bgra, void *stream);
+                             void *d_key, void *d_scratch, int64_t scratch_bytes, void *d_bgra, const float *clear_rgba,
+                             int clear_depth, uint32_t clear_depth_bits, void *stream);
 
 /* ---- textures  (rendering/_core.py:551-578 MemoryPool / create_texture2D, :94-96 sample2D) ---------
  * Point-sampled float4 CUDA texture object over caller-owned linear device memory (row 0 first).

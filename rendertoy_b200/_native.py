@@ -26,7 +26,7 @@ SIGNATURES = {
     "rt_raster_read_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_write_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_scratch_bytes": (_I64, [_I32, _I64, _I32, _I32]),
-    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _VP]),
+    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, _VP]),
     "rt_bvh_node_bytes": (_I64, [_I64]),
     "rt_bvh_tri_bytes": (_I64, [_I64]),
     "rt_bvh_scratch_bytes": (_I64, [_I64]),
@@ -93,3 +93,21 @@ def device_info():
 
 def float_array(values):
     return (C.c_float * len(values))(*[float(x) for x in values])
+
+
+_F4_CACHE = {}
+
+
+def float4_const(v):
+    """Cached (c_float * 4)(v, v, v, v)."""
+    a = _F4_CACHE.get(v)
+    if a is None:
+        a = _F4_CACHE[v] = (C.c_float * 4)(v, v, v, v)
+    return a
+
+
+def float_array_from_bytes(raw, n):
+    """(c_float * n) filled from a numpy uint8 view, one memmove."""
+    a = (C.c_float * n)()
+    C.memmove(a, raw.ctypes.data, 4 * n)
+    return a

@@ -535,6 +535,8 @@ struct ResolveArgs {
     int width, height;
     cudaTextureObject_t tex;
     int tex_w, tex_h;
+    int clear;         // 1: a clear(render_target) is folded into this draw ...
+    uint32_t clear_px; // ... pixels nobody wins get this BGRA8 value
 };
 
 struct PrimRec { float4 h1, h2, h3; };
@@ -603,6 +605,7 @@ __device__ __forceinline__ void resolve_pixel(const ResolveArgs &a, int x, int y
     }
     const float z = __uint_as_float(zbits);
     if (!(z <= 0)) a.bgra[p] = rt_pack_bgra(color.x, color.y, color.z, color.w); // FragmentProcess, :102
+    else if (a.clear) a.bgra[p] = a.clear_px;
     a.key[p] = k64 | 0xFFFFFFFFull; // re-arm: later draws win depth ties, as in the reference's draw order
 }
 
@@ -626,6 +629,7 @@ __global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
     for (int i = 0; i < 4; ++i) {
         const unsigned long long k64 = i == 0 ? k[0] : i == 1 ? k[1] : i == 2 ? k[2] : k[3];
         if ((unsigned)k64 != RT_NO_PRIMITIVE) resolve_pixel<SHADER>(a, x, y0 + 4 * i, k64);
+        else if (a.clear && y0 + 4 * i < a.height) a.bgra[(size_t)(y0 + 4 * i) * a.width + x] = a.clear_px;
     }
 }
 
@@ -659,6 +663,20 @@ __global__ void write_depth_kernel(unsigned long long *key, long long n, const u
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) key[i] = ((unsigned long long)in[i] << 32) | 0xFFFFFFFFull;
+}
+
+// host-side replica of rt_pack_bgra (sat, x255, round to nearest even)
+uint32_t pack_bgra_host(const float rgba[4])
+{
+    uint32_t px = 0;
+    const int order[4] = {2, 1, 0, 3};
+    for (int i = 0; i < 4; ++i) {
+        float v = rgba[order[i]] * 255.0f;
+        if (!(v > 0.0f)) v = 0.0f;
+        if (v > 255.0f) v = 255.0f;
+        px |= (uint32_t)__builtin_nearbyintf(v) << (8 * i);
+    }
+    return px;
 }
 
 int fill_grid(long long n_vec)
@@ -721,15 +739,7 @@ int rt_raster_clear_color(void *d_bgra, int64_t n_pixels, const float rgba[4], v
     RT_REQUIRE(d_bgra && rgba && n_pixels >= 0, "colour buffer");
     RT_REQUIRE(((uintptr_t)d_bgra & 15) == 0, "colour buffer must be 16-byte aligned");
     if (n_pixels == 0) return RT_OK;
-    // host-side replica of rt_pack_bgra (sat, x255, round to nearest even)
-    uint32_t px = 0;
-    const int order[4] = {2, 1, 0, 3};
-    for (int i = 0; i < 4; ++i) {
-        float v = rgba[order[i]] * 255.0f;
-        if (!(v > 0.0f)) v = 0.0f;
-        if (v > 255.0f) v = 255.0f;
-        px |= (uint32_t)__builtin_nearbyintf(v) << (8 * i);
-    }
+    const uint32_t px = pack_bgra_host(rgba);
     long long n4 = n_pixels / 4;
     fill_u32_kernel<<<fill_grid(n4), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_bgra, n4, px, (uint32_t *)d_bgra + 4 * n4,
                                                                     (int)(n_pixels - 4 * n4));
@@ -771,7 +781,8 @@ int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int 
 
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles, int shader,
                              const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_scratch,
-                             int64_t scratch_bytes, void *d_bgra, void *stream)
+                             int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth, uint32_t clear_depth_bits,
+                             void *stream)
 {
     RT_REQUIRE(n_triangles >= 0 && n_triangles < (1ll << 31), "triangle count (primitive ids are 32-bit: 2*t+k)");
     RT_REQUIRE(n_triangles == 0 || (d_pos4 && d_nrm4), "vertex arrays");
@@ -791,6 +802,12 @@ int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32
     ra.ctl = nullptr;
     ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
     ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
+    ra.clear = clear_rgba ? 1 : 0;
+    ra.clear_px = clear_rgba ? pack_bgra_host(clear_rgba) : 0u;
+    if (clear_depth) { // a pending clear(depth_buffer, v) folded into this call: must precede the coverage atomics
+        int rc = rt_raster_clear_depth(d_key, (int64_t)width * height, clear_depth_bits, stream);
+        if (rc != RT_OK) return rc;
+    }
     if (shader == RT_SHADER_LESSON09) {
         RT_REQUIRE(tex_handle != 0, "lesson09 shader needs a texture handle");
         const rt_texture *t = (const rt_texture *)(uintptr_t)tex_handle;

@@ -138,9 +138,16 @@ def device():
         "no CUDA device: rendertoy_b200 needs a B200 (set RENDERTOY_B200_HOST_BUFFERS=1 only to test host logic)")
 
 
+_DEV_INDEX = None
+
+
 def stream_ptr():
-    """cudaStream_t of torch's current stream, passed to every native call."""
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream, passed to every native call.  (torch.cuda.current_stream() costs
+    ~15 us of Python per call; the raw getter is ~0.3 us.  One process drives one GPU, so the index is cached.)"""
+    global _DEV_INDEX
+    if _DEV_INDEX is None:
+        _DEV_INDEX = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(_DEV_INDEX)
 
 
 class _Storage:
@@ -257,6 +264,14 @@ class DeviceBuffer:
 
     def map_to_host(self):
         return self.get()
+
+    def host_bytes(self):
+        """Read-only view of this buffer's bytes on the host without a copy when a valid host shadow exists
+        (small structs such as shader globals), else a fresh copy."""
+        st = self._st
+        if st.host is not None and st.host_valid:
+            return st.host[self.offset:self.offset + self.nbytes]
+        return st.read(self.offset, self.nbytes)
 
     def set(self, ary):
         ary = np.asarray(ary)
@@ -392,16 +407,39 @@ class Image:
         self.components, self.channel_dtype, self.is_bgra8 = _IMAGE_FORMATS[dtype]
         item = np.dtype(self.channel_dtype).itemsize * self.components
         nbytes = self.width * self.height * item
-        self.buffer = DeviceBuffer(_Storage(nbytes, tensor=memory), 0, (self.height, self.width, self.components),
-                                   np.dtype(self.channel_dtype))
+        self._buffer = DeviceBuffer(_Storage(nbytes, tensor=memory), 0, (self.height, self.width, self.components),
+                                    np.dtype(self.channel_dtype))
+        self._pending_clear = None   # rgba of a clear() not yet executed (BGRA8 targets only)
 
     @property
     def shape(self):
         return (self.width, self.height)  # pyopencl Image.shape is (width, height)
 
+    # clear(render_target) is deferred: Raster.draw_triangles folds it into its resolve kernel (no separate fill
+    # launch).  Any other access to the pixels executes it first, so the deferral is not observable.
+    def flush_clear(self):
+        if self._pending_clear is not None:
+            rgba, self._pending_clear = self._pending_clear, None
+            _native.call("rt_raster_clear_color", self._buffer.ptr, self.width * self.height, rgba, stream_ptr())
+            self._buffer.device_written()
+
+    def take_pending_clear(self):
+        rgba, self._pending_clear = self._pending_clear, None
+        return rgba
+
+    @property
+    def buffer(self):
+        self.flush_clear()
+        return self._buffer
+
     @property
     def ptr(self):
         return self.buffer.ptr
+
+    @property
+    def raw_ptr(self):
+        """Device address WITHOUT executing a deferred clear (for callers that consume take_pending_clear())."""
+        return self._buffer.ptr
 
     def get(self):
         """(H, W, C) array; BGRA8 images come back as uint8 bytes B,G,R,A."""
@@ -427,15 +465,29 @@ class DepthView:
         self.shape = (int(n_pixels),)
         self.dtype = np.dtype(np.uint32)
         self.size = int(n_pixels)
+        self._pending = None   # depth bits of a clear() not yet executed; the next draw (or any read) executes it
 
     def __len__(self):
         return self.size
 
-    def fill(self, bits):
+    def fill(self, bits, defer=False):
+        if defer:
+            self._pending = int(bits) & 0xFFFFFFFF
+            return
+        self._pending = None
         _native.call("rt_raster_clear_depth", self.key.ptr, self.size, int(bits) & 0xFFFFFFFF, stream_ptr())
         self.key.device_written()
 
+    def flush(self):
+        if self._pending is not None:
+            self.fill(self._pending)
+
+    def take_pending(self):
+        bits, self._pending = self._pending, None
+        return bits
+
     def get(self):
+        self.flush()
         out = torch.empty(self.size, dtype=torch.int32, device=self.key._st.tensor.device)
         _native.call("rt_raster_read_depth", self.key.ptr, self.size, out.data_ptr(), stream_ptr())
         return out.cpu().numpy().view(np.uint32)
@@ -443,6 +495,7 @@ class DepthView:
     map_to_host = get
 
     def set(self, ary):
+        self._pending = None
         ary = np.ascontiguousarray(ary, dtype=np.uint32).reshape(-1)
         src = torch.from_numpy(ary.view(np.int32)).to(self.key._st.tensor.device)
         _native.call("rt_raster_write_depth", self.key.ptr, self.size, src.data_ptr(), stream_ptr())
@@ -453,6 +506,12 @@ def clear(b, value=np.float32(0)):
     """Fill a buffer with a repeating value, or an image with a colour (rendering/_core.py:376-388).
     Deviation: for a sub-view the reference fills the whole underlying allocation (b.base_data); this fills
     the view only."""
+    if isinstance(b, DepthView) and isinstance(value, (float, np.float32)):      # clear(depth, 1.0): the per-frame call
+        b.fill(int(np.float32(value).view(np.uint32)), defer=True)
+        return
+    if isinstance(b, Image) and b.is_bgra8 and isinstance(value, (float, np.float32)):   # clear(render_target)
+        b._pending_clear = _native.float4_const(float(value))
+        return
     if isinstance(value, float):
         value = np.float32(value)
     if not isinstance(value, np.ndarray):
@@ -460,7 +519,7 @@ def clear(b, value=np.float32(0)):
     if isinstance(b, DepthView):
         pat = np.ascontiguousarray(value).reshape(-1).view(np.uint8)
         assert pat.size == 4, "depth buffer is cleared with one 32-bit value"
-        b.fill(int(pat.view(np.uint32)[0]))
+        b.fill(int(pat.view(np.uint32)[0]), defer=True)
         return
     if isinstance(b, DeviceBuffer):
         pat = np.ascontiguousarray(value).reshape(-1).view(np.uint8)
@@ -472,8 +531,7 @@ def clear(b, value=np.float32(0)):
         value = np.array([value] * 4)
     rgba = [float(x) for x in np.asarray(value, dtype=np.float32).reshape(-1)[:4]]
     if b.is_bgra8:
-        _native.call("rt_raster_clear_color", b.ptr, b.width * b.height, _native.float_array(rgba), stream_ptr())
-        b.buffer.device_written()
+        b._pending_clear = _native.float_array(rgba)
     else:
         px = np.asarray(rgba[:b.components], dtype=np.float32)
         b.buffer._st.write(0, np.tile(px, b.width * b.height))
@@ -489,10 +547,15 @@ def mapped(b: typing.Union[DeviceBuffer, Image, DepthView]):
             self.host = None
 
         def __enter__(self):
+            self.direct = False
             if isinstance(b, Image):
                 a = b.buffer.get()
                 self.host = a[..., 0] if b.components == 1 else a
                 self.raw = a
+            elif isinstance(b, DeviceBuffer) and b._st.host is not None and b._st.host_valid:
+                # small buffers (shader globals, descriptors): hand out the host shadow itself, no copies
+                self.direct = True
+                self.host = b._st.host[b.offset:b.offset + b.nbytes].view(b.dtype).reshape(b.shape)
             else:
                 self.host = b.get()
             return self.host
@@ -500,6 +563,9 @@ def mapped(b: typing.Union[DeviceBuffer, Image, DepthView]):
         def __exit__(self, exc_type, exc_val, exc_tb):
             if isinstance(b, Image):
                 b.buffer.set(self.raw)
+            elif self.direct:
+                b._st.dev_valid = False
+                b._st.version += 1
             else:
                 b.set(self.host)
             return False

@@ -86,6 +86,7 @@ class Raster:
 
         self.shader_id = self._resolve_builtin()
         self._scratch = None
+        self._scratch_tris = -1
         # kept for API compatibility with code that reads them (:378-380); nothing is sized by them here
         self.fragments_capacity = 32 * render_target.width * render_target.height
         self.primitive_capacity = 200000
@@ -129,9 +130,9 @@ class Raster:
         raise NotImplementedError("Raster.draw_points has no native kernel yet (SURVEY.md section 8f.3)")
 
     def _vs_globals(self):
-        g = self.vertex_shader_globals.get()
-        names = g.dtype.names
-        return np.concatenate([np.asarray(g[n]).reshape(-1).view(np.float32)[:16] for n in names[:3]]).astype(np.float32)
+        """48 floats (World, View, Proj) as a ctypes array: the Transforms struct is three contiguous float4x4 (layout
+        checked in _resolve_builtin), read straight from the struct's host shadow."""
+        return _native.float_array_from_bytes(self.vertex_shader_globals.host_bytes(), 48)
 
     def _texture_handle(self):
         if self.shader_id != _native.SHADER_LESSON09:
@@ -149,18 +150,20 @@ class Raster:
         if index_buffer is not None:
             assert index_buffer.dtype == np.int32, "index buffer must be int32 (_raster.py:154)"
             idx_ptr = index_buffer.ptr
+        depth_bits = self._depth_buffer.take_pending()     # a deferred clear(depth_buffer, v) rides along with this draw
         if not self._keys_armed:
             # first draw on a never-cleared target: give the zero-filled key buffer its NO_PRIMITIVE low words
-            if int(self._key_buffer.version) == 0:
-                self._depth_buffer.fill(0)
+            if depth_bits is None and int(self._key_buffer.version) == 0:
+                depth_bits = 0
             self._keys_armed = True
         rt = self._render_target
-        need = _native.lib().rt_raster_scratch_bytes(self.shader_id, primitive_count, rt.width, rt.height)
-        if self._scratch is None or self._scratch.nbytes < need:
+        if primitive_count > self._scratch_tris:
+            need = _native.lib().rt_raster_scratch_bytes(self.shader_id, primitive_count, rt.width, rt.height)
             self._scratch = create_buffer(int(need), np.uint8)   # zero-filled: the control block starts armed
-        g = self._vs_globals()
+            self._scratch_tris = primitive_count
         _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
-                     _native.float_array(g), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
-                     self._scratch.ptr, self._scratch.nbytes, rt.ptr, stream_ptr())
+                     self._vs_globals(), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
+                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, rt.take_pending_clear(),
+                     0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
         self._key_buffer.device_written()
-        rt.buffer.device_written()
+        rt._buffer.device_written()

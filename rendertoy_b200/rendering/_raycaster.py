@@ -178,10 +178,14 @@ class Raycaster:
         bgra_ptr = None
         if render_target is not None:
             assert render_target.is_bgra8, "render target must be the BGRA8 presenter image"
+            # a full-frame render overwrites every pixel: a deferred clear is dropped, otherwise executed first
+            if (x0, y0, w, h) == (0, 0, W, H):
+                render_target.take_pending_clear()
             bgra_ptr = render_target.ptr + 4 * (y0 * W + x0)
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
-                     self.nrm4.data_ptr(), self._idx_ptr(), _native.float_array(np.asarray(camera, np.float32).reshape(12)),
+                     self.nrm4.data_ptr(), self._idx_ptr(),
+                     _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12),
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
                      self.ctl.data_ptr(), None if stats is None else stats.data_ptr(), stream_ptr())
         if render_target is not None:
-            render_target.buffer.device_written()
+            render_target._buffer.device_written()

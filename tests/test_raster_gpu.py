@@ -54,3 +54,31 @@ def test_lesson_scene_matches_oracle(ren, oracle, lesson, width, height, n_tris,
         texf[:, :, 0:3] = tex / 255.0
     res = oracle.draw_triangles(lesson, width, height, rows, lessons.globals_as_floats(g), texture=texf)
     _compare(raster, res, f"lesson{lesson:02d} {width}x{height} T={rows.shape[0] // 3}")
+
+
+def test_deferred_clears_are_not_observable(ren, oracle):
+    """clear() of the render target / depth buffer is deferred into the next draw; any other access executes it first."""
+    w, h = 96, 64
+    pres = ren.create_presenter(w, h)
+    raster, g = lessons.build_lesson08(ren, pres.get_render_target())
+    target = raster.get_render_target()
+    ren.clear(target, np.array([1.0, 0.5, 0.25, 1.0], dtype=np.float32))
+    ren.clear(raster.get_depth_buffer(), 0.75)
+    assert (target.get() == np.array([64, 128, 255, 255], dtype=np.uint8)).all()            # B, G, R, A; 0.5*255 rounds to even
+    assert (raster.get_depth_buffer().get() == np.float32(0.75).view(np.uint32)).all()
+    # clear + draw: pixels nobody wins must carry the clear colour, winners the shaded colour
+    rows = scenes.dragon(1500)
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8, 0.5, w, h))
+    ren.clear(target, np.array([0.0, 0.0, 1.0, 1.0], dtype=np.float32))
+    ren.clear(raster.get_depth_buffer(), 1.0)
+    raster.draw_triangles(vb, None)
+    bg = np.zeros((h, w, 4), np.uint8); bg[:, :, 0] = 255; bg[:, :, 3] = 255
+    res = oracle.draw_triangles(8, w, h, rows, lessons.globals_as_floats(g), bgra=bg)
+    assert np.array_equal(target.get(), res.bgra) and (res.winner == 0xFFFFFFFF).any()
+    assert np.array_equal(raster.get_depth_buffer().get().reshape(h, w), res.depth)
+    # a second draw without clears composes on top (nothing pending any more)
+    raster.draw_triangles(vb, None)
+    assert np.array_equal(target.get(), res.bgra)

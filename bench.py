@@ -158,10 +158,11 @@ def bench_raycast(args, rank, world):
     rc = Raycaster([ren.Mesh(vb, None)])
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
-    store = parallel.FrameStore(n_frames, RAY_W, RAY_H) if (world > 1 and args.gather == "peer") else None
+    store = parallel.FrameStore(2 * n_frames, RAY_W, RAY_H) if (world > 1 and args.gather == "peer") else None
     fused = store is not None and store.ok
-    if fused:   # render targets ARE rank 0's frame store (peer-mapped): the kernel's BGRA8 stores are the gather
-        targets = [ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(k)) for k in my_frames]
+    if fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
+        targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k)) for k in my_frames] for b in range(2)]
+        targets = targets2[0]
         local = gathered = None
     else:
         targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]     # F x 33 MB > L2
@@ -171,10 +172,11 @@ def bench_raycast(args, rank, world):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * args.steps)]
 
     def step(s, timed_idx=None):
+        tg = targets2[s % 2] if fused else targets
         for j, k in enumerate(my_frames):
             if timed_idx is not None:
                 ev[timed_idx * F + j][0].record()
-            rc.render(targets[j], cams[s * n_frames + k])
+            rc.render(tg[j], cams[s * n_frames + k])
             if timed_idx is not None:
                 ev[timed_idx * F + j][1].record()
         collect()
@@ -258,7 +260,7 @@ def bench_raycast(args, rank, world):
                                "raycast 3840x2160, lesson06 camera orbit, primary rays + closest hit + Lambert shade",
                    "frames_per_rank_per_step": F,
                    "partition": "frames k = rank (mod N); " + ("every rank's kernel stores its pixels straight into rank 0's frame store "
-                                "over NVLink (CUDA IPC peer memory), one barrier per step" if fused else
+                                "over NVLink (CUDA IPC peer memory, double-buffered), one stream-ordered 4-byte all-reduce per step" if fused else
                                 "framebuffers gathered to rank 0 with NCCL send/recv" if world > 1 else "single GPU, no gather"),
                    "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
                          "L2-resident by design, as they are reused every frame",
@@ -299,13 +301,15 @@ def bench_raster(args, rank, world, rows=None):
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
     # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
-    store = parallel.FrameStore(n_frames, RAS_W, RAS_H) if (world > 1 and args.gather == "peer") else None
+    store = parallel.FrameStore(2 * n_frames, RAS_W, RAS_H) if (world > 1 and args.gather == "peer") else None
     fused = store is not None and store.ok
-    rasters = []
+    rasters, rasters_b = [], []
     for j in range(F):
         target = ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(my_frames[j])) if fused else \
             ren.create_presenter(RAS_W, RAS_H).get_render_target()
         rasters.append(lessons.build_lesson08(ren, target))
+        if fused:   # second half of the double-buffered frame store
+            rasters_b.append(lessons.build_lesson08(ren, ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(n_frames + my_frames[j]))))
     local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (world > 1 and not fused) else None
     gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1 and not fused) else None
     cams = {k: scenes.lesson_camera(ren, 8, orbit_t(k), RAS_W, RAS_H) for k in range(n_frames * (args.steps + args.warmup + 6))}
@@ -315,8 +319,8 @@ def bench_raster(args, rank, world, rows=None):
     streams = [torch.cuda.Stream() for _ in range(F)] if args.raster_streams else None
     main_stream = torch.cuda.current_stream()
 
-    def frame(j, k):
-        raster, g = rasters[j]
+    def frame(j, k, odd=False):
+        raster, g = rasters_b[j] if (odd and fused) else rasters[j]
         if streams is None:
             lessons.set_transforms(ren, g, *cams[k])
             lessons.render_frame(ren, raster, vb)
@@ -347,7 +351,7 @@ def bench_raster(args, rank, world, rows=None):
     def step(s):
         fork()
         for j, k in enumerate(my_frames):
-            frame(j, s * n_frames + k)
+            frame(j, s * n_frames + k, odd=bool(s & 1))
         join()
         gather()
 

@@ -132,6 +132,7 @@ class FrameStore:
             ok = all(flags)
         self.ok = ok and self._base is not None
         self.memory = torch.as_tensor(_RawDeviceMemory(self._base, nbytes), device="cuda") if self.ok else None
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
 
     def frame(self, k):
         """uint8 view (frame_bytes,) of frame k."""
@@ -142,9 +143,12 @@ class FrameStore:
         return self.memory.view(torch.int32).view(self.n_frames, self.height, self.width)
 
     def commit(self):
-        """All ranks' kernels writing into the store have finished once every rank passes this barrier."""
+        """Stream-ordered barrier: a 4-byte all-reduce enqueued behind this rank's rendering kernels.  Work enqueued
+        after it (on any rank) runs only once every rank's kernels that wrote into the store have finished; the host
+        is not blocked, so consecutive batches keep pipelining.  Re-use a slot only two commits later (double-buffer
+        the store), so rank `dst` has consumed it in between."""
         if self.world > 1:
-            dist.barrier()
+            dist.all_reduce(self._flag)
 
     def close(self):
         if self._base is None:

@@ -120,11 +120,14 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * row-major: d_hits (16 B/pixel, may be NULL), d_bgra (4 B/pixel, may be NULL; row pitch `bgra_pitch_px`
  * pixels, so a rank can write its tile straight into a full frame).  shader selects the lesson08 / lesson09
  * shading; d_pos4 / tex_handle are only needed for lesson09.  d_stats: NULL, or 3 x uint64 that an instrumented
- * build of the kernel ADDS {inner-node visits, triangle tests, rays} to (for the roofline report; slower). */
+ * build of the kernel ADDS {inner-node visits, triangle tests, rays} to (for the roofline report; slower).
+ * cull_rect: NULL, or 4 ints {x0, y0, x1, y1} (inclusive, frame pixels): a conservative screen-space bound of the
+ * scene the caller computed; pixels outside are written as misses without tracing.  fast_slab: non-zero lets the
+ * box tests use the FMA form (caller guarantees the origin is within 16 scene extents of the scene). */
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
-                       int64_t bgra_pitch_px, void *d_ctl, void *d_stats, void *stream);
+                       int64_t bgra_pitch_px, void *d_ctl, void *d_stats, const int *cull_rect, int fast_slab, void *stream);
 
 /* ---- multi-GPU frame store  (no reference counterpart: rendering/_core.py:10-11 is single-device) -------
  * Rank 0 allocates the store (cudaMalloc, IPC-exportable) and exports a 64-byte handle; the other ranks of the

@@ -40,15 +40,20 @@ struct TraceArgs {
     cudaTextureObject_t tex;
     int tex_w, tex_h;
     unsigned *ctl; // [0] next work unit, [1] finished blocks; both zero between launches
+    int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
 
 struct Hit { float t, u, v; unsigned id; };
 
-template <bool STATS>
+template <bool STATS, bool FMA>
 __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, float oz, float dx, float dy, float dz, int *stack /* [STACK], per thread */)
 {
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    // FMA form of the slab test, t = lo * inv - o * inv: half the FP32 instructions.  Only conservativeness matters for
+    // box tests (hits are decided by the exact Moller-Trumbore below); the launcher enables it when the ray origin is
+    // within 16 scene extents, where its rounding error (<= 2^-19 extent in box space) stays inside the 2^-17 padding.
+    const float oix = ox * ix, oiy = oy * iy, oiz = oz * iz;
     unsigned long long best = ~0ull;
     float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
     int sp = 0, cur = 0;
@@ -60,12 +65,20 @@ __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, flo
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             const int4 n3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
             // fminf/fmaxf drop NaN (0 * inf on a slab face): conservative
-            float a0 = (n0.x - ox) * ix, b0 = (n0.y - ox) * ix, c0 = (n0.z - oy) * iy, d0 = (n0.w - oy) * iy;
-            float e0 = (n2.x - oz) * iz, f0 = (n2.y - oz) * iz;
+            float a0, b0, c0, d0, e0, f0, a1, b1, c1, d1, e1, f1;
+            if (FMA) {
+                a0 = __fmaf_rn(n0.x, ix, -oix); b0 = __fmaf_rn(n0.y, ix, -oix); c0 = __fmaf_rn(n0.z, iy, -oiy); d0 = __fmaf_rn(n0.w, iy, -oiy);
+                e0 = __fmaf_rn(n2.x, iz, -oiz); f0 = __fmaf_rn(n2.y, iz, -oiz);
+                a1 = __fmaf_rn(n1.x, ix, -oix); b1 = __fmaf_rn(n1.y, ix, -oix); c1 = __fmaf_rn(n1.z, iy, -oiy); d1 = __fmaf_rn(n1.w, iy, -oiy);
+                e1 = __fmaf_rn(n2.z, iz, -oiz); f1 = __fmaf_rn(n2.w, iz, -oiz);
+            } else {
+                a0 = (n0.x - ox) * ix; b0 = (n0.y - ox) * ix; c0 = (n0.z - oy) * iy; d0 = (n0.w - oy) * iy;
+                e0 = (n2.x - oz) * iz; f0 = (n2.y - oz) * iz;
+                a1 = (n1.x - ox) * ix; b1 = (n1.y - ox) * ix; c1 = (n1.z - oy) * iy; d1 = (n1.w - oy) * iy;
+                e1 = (n2.z - oz) * iz; f1 = (n2.w - oz) * iz;
+            }
             float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(c0, d0)), fmaxf(fminf(e0, f0), 0.0f));
             float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(c0, d0)), fminf(fmaxf(e0, f0), tbest));
-            float a1 = (n1.x - ox) * ix, b1 = (n1.y - ox) * ix, c1 = (n1.z - oy) * iy, d1 = (n1.w - oy) * iy;
-            float e1 = (n2.z - oz) * iz, f1 = (n2.w - oz) * iz;
             float tn1 = fmaxf(fmaxf(fminf(a1, b1), fminf(c1, d1)), fmaxf(fminf(e1, f1), 0.0f));
             float tf1 = fminf(fminf(fmaxf(a1, b1), fmaxf(c1, d1)), fminf(fmaxf(e1, f1), tbest));
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
@@ -140,7 +153,7 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 }
 
 // MODE 0: rays from a buffer, hits out.  MODE 8 / 9: primary rays + shade with that lesson's shader.
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool FMA>
 __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
 {
     int stack[STACK];
@@ -150,7 +163,8 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
     const long long n_units = MODE ? (long long)tiles_x * ((a.h + 3) >> 2) : (a.n_rays + 31) >> 5;
     const float two_over_w = MODE ? 2.0f / (float)a.width : 0.0f, two_over_h = MODE ? 2.0f / (float)a.height : 0.0f;
 
-    // (claiming the next unit early, to hide the atomic's L2 round trip, measured 6 % SLOWER on B200: not done)
+    // (claiming the next unit early to hide the atomic's L2 round trip measured 6 % SLOWER on B200, and carrying entry
+    //  distances on the stack to drop stale subtrees at pop time 10 % slower: neither is done)
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(a.ctl, 1u);
@@ -165,7 +179,13 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
             const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
             const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
             const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
-            const Hit h = trace<STATS>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+            Hit h;
+            const int gx = a.x0 + lx, gy = a.y0 + ly;
+            if (gx < a.cull[0] || gy < a.cull[1] || gx > a.cull[2] || gy > a.cull[3]) {
+                h.t = INFINITY; h.u = 0.0f; h.v = 0.0f; h.id = 0xFFFFFFFFu; // outside the scene's screen bounds: a miss
+            } else {
+                h = trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+            }
             const long long p = (long long)ly * a.w + lx;
             if (a.hits) a.hits[p] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
             if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
@@ -173,7 +193,7 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
             const long long r = (long long)unit * 32 + lane;
             if (r >= a.n_rays) continue;
             const float4 o = __ldg(a.rays + 2 * r), d = __ldg(a.rays + 2 * r + 1);
-            const Hit h = trace<STATS>(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
+            const Hit h = trace<STATS, false>(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
             a.hits[r] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
         }
     }
@@ -185,20 +205,21 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
     }
 }
 
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool FMA>
 int launch_trace_s(const TraceArgs &a, cudaStream_t st)
 {
-    int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<MODE, STATS>, TB, 0));
-    raycast_kernel<MODE, STATS><<<rt_sm_count() * (per_sm > 0 ? per_sm : 1), TB, 0, st>>>(a);
+    static int per_sm = 0; // per instantiation; the occupancy query costs ~10 us of host time
+    if (per_sm == 0) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<MODE, STATS, FMA>, TB, 0));
+    raycast_kernel<MODE, STATS, FMA><<<rt_sm_count() * (per_sm > 0 ? per_sm : 1), TB, 0, st>>>(a);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
 
 template <int MODE>
-int launch_trace(const TraceArgs &a, cudaStream_t st)
+int launch_trace(const TraceArgs &a, bool fma, cudaStream_t st)
 {
-    return a.stats ? launch_trace_s<MODE, true>(a, st) : launch_trace_s<MODE, false>(a, st);
+    if (a.stats) return fma ? launch_trace_s<MODE, true, true>(a, st) : launch_trace_s<MODE, true, false>(a, st);
+    return fma ? launch_trace_s<MODE, false, true>(a, st) : launch_trace_s<MODE, false, false>(a, st);
 }
 
 } // namespace
@@ -216,13 +237,13 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
     TraceArgs a = {};
     a.nodes = (const RtBvhNode *)d_nodes; a.tris = (const RtBvhTri *)d_tris;
     a.rays = (const float4 *)d_rays; a.n_rays = n_rays; a.hits = (float4 *)d_hits; a.ctl = (unsigned *)d_ctl;
-    return launch_trace<0>(a, (cudaStream_t)stream);
+    return launch_trace<0>(a, false, (cudaStream_t)stream);
 }
 
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4, const void *d_nrm4,
                        const int32_t *d_indices, const float *camera, int width, int height, int x0, int y0, int w, int h, int shader,
                        uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_ctl, void *d_stats,
-                       void *stream)
+                       const int *cull_rect, int fast_slab, void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
     RT_REQUIRE(camera && d_ctl, "camera / control block");
@@ -238,15 +259,17 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     a.hits = (float4 *)d_hits; a.bgra = (uint32_t *)d_bgra; a.pitch_px = bgra_pitch_px;
     a.pos = (const float4 *)d_pos4; a.nrm = (const float4 *)d_nrm4; a.idx = d_indices; a.ctl = (unsigned *)d_ctl;
     a.stats = (unsigned long long *)d_stats;
+    a.cull[0] = cull_rect ? cull_rect[0] : 0; a.cull[1] = cull_rect ? cull_rect[1] : 0;
+    a.cull[2] = cull_rect ? cull_rect[2] : width - 1; a.cull[3] = cull_rect ? cull_rect[3] : height - 1;
     if (shader == RT_SHADER_LESSON09) {
         RT_REQUIRE(!d_bgra || (tex_handle != 0 && d_pos4), "lesson09 shading needs a texture handle and positions");
         if (tex_handle) {
             const rt_texture *t = (const rt_texture *)(uintptr_t)tex_handle;
             a.tex = t->obj; a.tex_w = t->w; a.tex_h = t->h;
         }
-        return launch_trace<9>(a, (cudaStream_t)stream);
+        return launch_trace<9>(a, fast_slab != 0, (cudaStream_t)stream);
     }
-    return launch_trace<8>(a, (cudaStream_t)stream);
+    return launch_trace<8>(a, fast_slab != 0, (cudaStream_t)stream);
 }
 
 } // extern "C"

@@ -114,6 +114,11 @@ class Raycaster:
                 self.indices = torch.cat(parts).to(torch.int32)
             else:
                 self.indices = None
+        # scene bounds on the host (one sync at build time): used for the screen-space cull rect and the FMA-slab guard
+        xyz = self.pos4[:, :3]
+        self.scene_lo = xyz.amin(0).double().cpu().numpy()
+        self.scene_hi = xyz.amax(0).double().cpu().numpy()
+        self.scene_extent = float((self.scene_hi - self.scene_lo).max())
         dev = self.pos4.device
         L = _native.lib()
         n = self.n_triangles
@@ -158,14 +163,32 @@ class Raycaster:
         out.device_written()
         return out
 
+    def screen_bounds(self, camera, W, H):
+        """Conservative inclusive pixel rect [x0, y0, x1, y1] containing every pixel whose primary ray can hit the
+        scene's bounding box (projected corners +- 2 px), or None when the box reaches behind the eye."""
+        cam = np.asarray(camera, np.float64).reshape(4, 3)
+        o, basis = cam[0], cam[1:4].T                      # columns U, V, W: p - o = a*U + b*V + c*W
+        lo, hi = self.scene_lo, self.scene_hi
+        corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+        try:
+            abc = np.linalg.solve(basis, (corners - o).T)
+        except np.linalg.LinAlgError:
+            return None
+        if not np.all(np.isfinite(abc)) or abc[2].min() <= 1e-6 * max(self.scene_extent, 1e-30):
+            return None
+        px = (abc[0] / abc[2] + 1.0) * (W * 0.5) - 0.5
+        py = (1.0 - abc[1] / abc[2]) * (H * 0.5) - 0.5
+        return (int(max(0, np.floor(px.min()) - 2)), int(max(0, np.floor(py.min()) - 2)),
+                int(min(W - 1, np.ceil(px.max()) + 2)), int(min(H - 1, np.ceil(py.max()) + 2)))
+
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
-               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None):
+               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True):
         """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
         shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
         hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
         hits are wanted (then frame_size=(W, H) is required).  stats: optional int64[3] tensor; the instrumented kernel
-        adds {node visits, triangle tests, rays} to it."""
+        adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds."""
         if render_target is not None:
             W, H = render_target.width, render_target.height
         else:
@@ -182,10 +205,18 @@ class Raycaster:
             if (x0, y0, w, h) == (0, 0, W, H):
                 render_target.take_pending_clear()
             bgra_ptr = render_target.ptr + 4 * (y0 * W + x0)
+        cam32 = np.ascontiguousarray(camera, np.float32).reshape(12)
+        rect_c = None
+        if cull:
+            r = self.screen_bounds(cam32, W, H)
+            if r is not None:
+                import ctypes
+                rect_c = (ctypes.c_int * 4)(*r)
+        fast_slab = int(float(np.abs(cam32[0:3]).max()) <= 16.0 * self.scene_extent)
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
                      self.nrm4.data_ptr(), self._idx_ptr(),
-                     _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12),
+                     _native.float_array_from_bytes(cam32.view(np.uint8), 12),
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
-                     self.ctl.data_ptr(), None if stats is None else stats.data_ptr(), stream_ptr())
+                     self.ctl.data_ptr(), None if stats is None else stats.data_ptr(), rect_c, fast_slab, stream_ptr())
         if render_target is not None:
             render_target._buffer.device_written()

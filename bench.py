@@ -251,7 +251,7 @@ def bench_raycast(args, rank, world):
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     sm_count = torch.cuda.get_device_properties(0).multi_processor_count
     fp32_peak = sm_count * 128 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
-    flops = (nodes * 2 * 22 + tests * 45) * (RAY_W * RAY_H / max(rays, 1))
+    flops = nodes * 2 * 22 + tests * 45          # totals of one full instrumented frame (culled pixels trace nothing)
     out = {
         "metric": METRIC_RAY, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -272,7 +272,8 @@ def bench_raycast(args, rank, world):
                              "L1/L2 latency, see fp32 and profiles/",
                      "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
-                              "inner_node_visits_per_ray": nodes / max(rays, 1), "triangle_tests_per_ray": tests / max(rays, 1),
+                              "inner_node_visits_per_ray": nodes / (RAY_W * RAY_H), "triangle_tests_per_ray": tests / (RAY_W * RAY_H),
+                              "rays_traced_fraction": rays / (RAY_W * RAY_H),
                               "flop_model": "44 flop per inner node (2 slab tests) + 45 flop per Moller-Trumbore test; peak counts "
                                             "FMA as 2 flop, this kernel is compiled -fmad=false for bit-exact parity"}},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": 4 * RAY_W * RAY_H * F,

@@ -129,6 +129,16 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
                        int64_t bgra_pitch_px, void *d_ctl, void *d_stats, const int *cull_rect, int fast_slab, void *stream);
 
+/* ---- run-time kernels  (rendering/_core.py:247-299: kernel_main / build_kernel_main, one OpenCL program built at
+ * first dispatch) --------------------------------------------------------------------------------------------
+ * cuda_source: CUDA C++ produced from the user's OpenCL C by rendering/_dsl.py.  Compiled with NVRTC for sm_100a
+ * (no FMA contraction); compile works without a GPU, launch needs one.  On a build error the compiler log is copied
+ * to `log`.  rt_dsl_launch runs `kernel` over n_threads work-items, 1-D; args[i] points at the i-th argument's value
+ * (device pointer for buffers, raw bytes for by-value structs/scalars), the trailing `int number_of_threads` included. */
+int rt_dsl_compile(const char *cuda_source, uint64_t *out_module, char *log, int log_cap);
+int rt_dsl_launch(uint64_t module, const char *kernel, int64_t n_threads, void **args, void *stream);
+int rt_dsl_unload(uint64_t module);
+
 /* ---- multi-GPU frame store  (no reference counterpart: rendering/_core.py:10-11 is single-device) -------
  * Rank 0 allocates the store (cudaMalloc, IPC-exportable) and exports a 64-byte handle; the other ranks of the
  * node open it and pass addresses inside it as `d_bgra` to rt_raycast_primary / rt_raster_draw_triangles /

@@ -124,6 +124,17 @@ template <typename V, typename T, int S, int... I> inline V operator-(const SwzI
 inline float2 operator*(const float2 &a, int b) { return a * (float)b; }
 inline float3 operator*(const float3 &a, int b) { return a * (float)b; }
 
+// relational operators (OpenCL: -1 per true lane) + any(), as used by the tutorials' clip tests
+struct alignas(16) int3 { union { int s[4]; struct { int x, y, z; }; }; };
+#define REL_OPS(OPNAME, OP)                                                                                                   \
+    inline int3 OPNAME(const float3 &a, const float3 &b) { int3 r; for (int i = 0; i < 3; ++i) r.s[i] = (a.s[i] OP b.s[i]) ? -1 : 0; r.s[3] = 0; return r; } \
+    inline int3 OPNAME(const float3 &a, double b) { int3 r; for (int i = 0; i < 3; ++i) r.s[i] = (a.s[i] OP (float)b) ? -1 : 0; r.s[3] = 0; return r; }     \
+    template <int S, int... I> inline int3 OPNAME(const SwzImpl<float3, float, S, I...> &a, const float3 &b) { return OPNAME(float3(a), b); }                \
+    template <int S, int... I> inline int3 OPNAME(const SwzImpl<float3, float, S, I...> &a, double b) { return OPNAME(float3(a), b); }
+REL_OPS(operator<, <) REL_OPS(operator>, >) REL_OPS(operator<=, <=) REL_OPS(operator>=, >=)
+inline int any(const int3 &v) { return (v.x | v.y | v.z) < 0; }
+inline float3 operator+(const float3 &a, double b) { return a + (float)b; }
+
 // ---- "(floatN)(...)" constructors (translate.py rewrites the cast syntax to these) -----------------------
 inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 inline float2 make_float2(float a) { return make_float2(a, a); }

@@ -138,6 +138,27 @@ def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=N
     return depth_bad, colour_bad_notie
 
 
+def run_lesson06_splat(out_dir):
+    """tutorials/lesson06_loading_obj.py:29-54: the @kernel_main point splat, run verbatim through the shim."""
+    path = f"{REFERENCE}/tutorials/lesson06_loading_obj.py"
+    ns = tutorial_definitions(path)          # Transforms struct + transform_and_draw kernel (decorated definitions only)
+    w, h = 160, 120
+    rows = scenes.dragon(1500)
+    vb = upload_mesh(rows)
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    info = ren.create_struct(ns["Transforms"])
+    W, V, P = hm.matmul(hm.scale(1.0), hm.rotate(0.7, (0, 1, 0))), hm.look_at((0, 0.3, 2), (0, 0, 0), (0, 1, 0)), hm.perspective(aspect_ratio=w / h)
+    set_globals(info, W, V, P)
+    ren.clear(target)
+    ns["transform_and_draw"][vb.shape](target, vb, info)
+    with ren.mapped(target) as m:
+        bgra = np.array(m).view(np.uint8).reshape(h, w, 4).copy()
+    print(f"dsl_lesson06: {int((bgra[:, :, 3] != 0).sum())} pixels written by the reference's own kernel")
+    np.savez_compressed(os.path.join(out_dir, "dsl_lesson06.npz"), rows=rows, width=w, height=h,
+                        globals=np.concatenate([W.ravel(), V.ravel(), P.ravel()]).astype(np.float32), bgra=bgra)
+    return 0, 0
+
+
 def cases():
     rng = np.random.default_rng(7)
     tex = rng.integers(0, 256, size=(17, 23, 3), dtype=np.uint8)
@@ -170,10 +191,13 @@ def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        if sys.argv[2] == "dsl_lesson06":
+            run_lesson06_splat(out_dir)
+            return 0
         r = run_case(sys.argv[2], out_dir=out_dir, **cases()[sys.argv[2]])
         return 0 if r is None or (r[0] == 0 and r[1] == 0) else 1
     import subprocess
-    bad = [n for n in cases() if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
+    bad = [n for n in list(cases()) + ["dsl_lesson06"] if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
     print("ORACLE PINNED: every depth word and every non-tie colour matches the reference run" if not bad else f"MISMATCH in {bad}")
     return 0 if not bad else 1
 

@@ -4,7 +4,7 @@ import sys as _sys
 
 from rendertoy_b200 import rendering as _impl
 from rendertoy_b200.rendering import *  # noqa: F401,F403
-from rendertoy_b200.rendering import _core, _modeling, _loaders, _presentation, _raster, _raycaster  # noqa: F401
+from rendertoy_b200.rendering import _core, _modeling, _loaders, _presentation, _raster, _raycaster, _dsl  # noqa: F401
 
 for _name in ("_core", "_modeling", "_loaders", "_presentation", "_raster", "_raycaster", "_dsl"):
     _mod = _sys.modules.get(f"rendertoy_b200.rendering.{_name}")

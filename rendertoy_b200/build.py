@@ -75,7 +75,7 @@ def build_native(force=False, verbose=False):
     objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in sources()]
     if jobs or force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *_host_compiler_args(), "-o", LIB_PATH, *objs,
-               "-cudart", "static"]
+               "-cudart", "static", "-ldl"]
         run(cmd)
     return LIB_PATH
 

@@ -21,4 +21,4 @@ from ._raster import Raster
 
 from ._raycaster import Raycaster
 
-from . import _core, _modeling, _loaders, _presentation, _raster, _raycaster
+from . import _core, _modeling, _loaders, _presentation, _raster, _raycaster, _dsl

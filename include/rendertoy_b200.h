@@ -92,6 +92,16 @@ int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32
                              void *d_key, void *d_scratch, int64_t scratch_bytes, void *d_bgra, const float *clear_rgba,
                              int clear_depth, uint32_t clear_depth_bits, void *stream);
 
+/* ---- Raster.draw_points  (rendering/_raster.py:399-414) -----------------------------------------------------
+ * VertexProcess + PointAssembly (z<0 cull, :140-151) + PointRaster (clip-space |x|,|y| <= w, :214-226) + Dehomogenize +
+ * DepthTest + FragmentProcess as two kernels (per-point depth atomics, per-pixel resolve).  Arguments as for
+ * rt_raster_draw_triangles; d_indices (int32 or NULL) selects the vertex of each point; point id = list position. */
+int64_t rt_raster_points_scratch_bytes(int64_t n_points);
+int rt_raster_draw_points(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_points, int shader,
+                          const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key,
+                          void *d_scratch, int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth,
+                          uint32_t clear_depth_bits, void *stream);
+
 /* ---- textures  (rendering/_core.py:551-578 MemoryPool / create_texture2D, :94-96 sample2D) ---------
  * Point-sampled float4 CUDA texture object over caller-owned linear device memory (row 0 first).
  * d_texels must be 512-byte aligned. */

@@ -104,6 +104,28 @@ def draw_triangles(shader, width, height, mesh_vertices, vs_globals, indices=Non
     return RasterResult(depth, bgra, winner, tie, {n: int(getattr(st, n)) for n, _ in _Stats._fields_})
 
 
+def draw_points(shader, width, height, mesh_vertices, vs_globals, indices=None, texture=None, depth=None, bgra=None):
+    """One Raster.draw_points (rendering/_raster.py:399-414) on cleared (or supplied) targets."""
+    L = lib()
+    mesh = _mesh_rows(mesh_vertices)
+    g = np.ascontiguousarray(np.asarray(vs_globals, dtype=np.float32).reshape(48))
+    idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+    n_points = mesh.shape[0] if idx is None else idx.shape[0]
+    depth = np.full((height, width), 0x3F800000, dtype=np.uint32) if depth is None else np.ascontiguousarray(depth, dtype=np.uint32).copy()
+    bgra = np.zeros((height, width, 4), dtype=np.uint8) if bgra is None else np.ascontiguousarray(bgra, dtype=np.uint8).copy()
+    winner = np.full((height, width), NO_WINNER, dtype=np.uint32)
+    cfg = _Config(shader, width, height, _fp(g), None, 0, 0)
+    tex = None
+    if texture is not None:
+        tex = np.ascontiguousarray(texture, dtype=np.float32)
+        cfg.tex, cfg.tex_h, cfg.tex_w = _fp(tex), tex.shape[0], tex.shape[1]
+    st = _Stats()
+    rc = L.orc_draw_points(C.byref(cfg), _fp(mesh), _p(idx, C.c_int32), C.c_int64(n_points), C.c_int64(mesh.shape[0]),
+                           _p(depth, C.c_uint32), _p(bgra, C.c_uint8), _p(winner, C.c_uint32), C.byref(st))
+    assert rc == 0
+    return RasterResult(depth, bgra, winner, np.zeros((height, width), np.uint8), {n: int(getattr(st, n)) for n, _ in _Stats._fields_})
+
+
 def vertex_kat(P, vs_globals, width, height):
     g = np.ascontiguousarray(np.asarray(vs_globals, dtype=np.float32).reshape(48))
     p = np.ascontiguousarray(P, dtype=np.float32)

@@ -74,7 +74,7 @@ def _alarm(*_):
     raise Timeout()
 
 
-def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=None, out_dir=None):
+def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=None, out_dir=None, points=False):
     """One frame: clear, clear, then one draw per entry of rows_list (draws compose on the same targets)."""
     lesson_file = f"{REFERENCE}/tutorials/lesson{lesson:02d}_" + ("rasterization.py" if lesson == 8 else "texture_mapping.py")
     ns = tutorial_definitions(lesson_file)
@@ -106,7 +106,10 @@ def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=N
     try:
         for rows, idx in zip(rows_list, indices_list):
             ib = None if idx is None else ren.create_buffer_from(np.asarray(idx, np.int32))
-            raster.draw_triangles(upload_mesh(rows), ib)
+            if points:
+                raster.draw_points(upload_mesh(rows), ib)
+            else:
+                raster.draw_triangles(upload_mesh(rows), ib)
     except Timeout:
         print(f"{name}: reference did not terminate (latent hang of the `while` at _raster.py:428); case skipped")
         return None
@@ -119,7 +122,8 @@ def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=N
     od, ob, tie_any = None, None, np.zeros((h, w), np.uint8)
     stats = []
     for rows, idx in zip(rows_list, indices_list):
-        r = oracle.draw_triangles(lesson, w, h, rows, gl, indices=idx, texture=texf, depth=od, bgra=ob)
+        draw = oracle.draw_points if points else oracle.draw_triangles
+        r = draw(lesson, w, h, rows, gl, indices=idx, texture=texf, depth=od, bgra=ob)
         od, ob = r.depth, r.bgra
         tie_any |= r.tie
         stats.append(r.stats)
@@ -130,7 +134,7 @@ def run_case(name, lesson, rows_list, w, h, eye, t, texture=None, indices_list=N
     print(f"{name}: {w}x{h} draws={len(rows_list)} covered={covered} depth_mismatch={depth_bad} colour_mismatch={int(colour_bad.sum())} "
           f"(outside depth ties: {colour_bad_notie}) tie_pixels={int(tie_any.sum())} stats={stats}")
     if out_dir:
-        np.savez_compressed(os.path.join(out_dir, f"raster_{name}.npz"), lesson=lesson, width=w, height=h, globals=gl,
+        np.savez_compressed(os.path.join(out_dir, f"raster_{name}.npz"), lesson=lesson, width=w, height=h, globals=gl, points=int(points),
                             n_draws=len(rows_list), texture=texf if texf is not None else np.zeros(0, np.float32),
                             depth=depth, bgra=bgra, tie=tie_any,
                             **{f"rows{i}": r for i, r in enumerate(rows_list)},
@@ -181,6 +185,10 @@ def cases():
         "l08_nearclip": dict(lesson=8, rows_list=[scenes.dragon(800)], w=128, h=96, eye=(0.12, 0.32, 0.3), t=4.5),
         "l09_nearclip": dict(lesson=9, rows_list=[scenes.dragon(800)], w=128, h=96, eye=(0.12, 0.32, 0.3), t=4.5, texture=tex),
         # two draws composing on one depth/colour target, the second one indexed
+        # Raster.draw_points (_raster.py:399-414), soup and indexed.  Indices stay below len(indices): the reference runs
+        # its vertex kernel over only that many vertices (:400-403, likewise :419-421), anything above reads stale memory.
+        "l08_points": dict(lesson=8, rows_list=[scenes.dragon(900), scenes.dragon(700, seed=5)], w=120, h=90, eye=(0, 0.3, 1.0), t=0.4,
+                           indices_list=[None, rng.integers(0, 1500, 1500).astype(np.int32)], points=True),
         "l08_two_draws_indexed": dict(lesson=8, rows_list=[a, b], w=144, h=108, eye=(0, 0.3, 1.0), t=0.9, indices_list=[None, idx]),
     }
 

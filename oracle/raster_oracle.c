@@ -404,6 +404,70 @@ int orc_draw_triangles(const orc_config *cfg, const float *mesh_vertices, const 
     return 0;
 }
 
+/* Raster.draw_points, _raster.py:399-414: VertexProcess -> PointAssembly (z<0 cull, :140-151) -> PointRaster
+ * (|x|,|y| <= w clip on CLIP-space coordinates, :214-226) -> Dehomogenize -> DepthTest -> FragmentProcess.
+ * Point id = position in the (optionally indexed) point list; ties go to the lowest id.  Fragments landing on
+ * px == W or py == H (x == w exactly) are dropped (the reference would write out of bounds). */
+int orc_draw_points(const orc_config *cfg, const float *mesh_vertices, const int32_t *indices, int64_t n_points, int64_t n_vertices,
+                    uint32_t *depth, uint8_t *bgra, uint32_t *winner, orc_stats *stats)
+{
+    const int st = orc_stride(cfg->shader), W = cfg->width, H = cfg->height;
+    orc_stats S; memset(&S, 0, sizeof S);
+    S.triangles_in = n_points;
+    float *vb = (float *)malloc(sizeof(float) * (size_t)st * (size_t)(n_vertices > 0 ? n_vertices : 1));
+    orc_vertex_process(cfg->shader, mesh_vertices, n_vertices, cfg->vs_globals, vb);
+    float *frag = (float *)malloc(sizeof(float) * (size_t)st * (size_t)(n_points > 0 ? n_points : 1));
+    uint8_t *alive = (uint8_t *)calloc((size_t)(n_points > 0 ? n_points : 1), 1);
+    const float half_w = (float)W * 0.5f, half_h = (float)H * 0.5f;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_points; ++i) {
+        const float *v = vb + (size_t)st * (indices ? indices[i] : i);
+        if (v[2] < 0) continue;                                                   /* PointAssembly */
+        if (v[0] < -v[3] || v[0] > v[3] || v[1] < -v[3] || v[1] > v[3]) continue; /* PointRaster   */
+        float *f = frag + (size_t)st * i;
+        memcpy(f, v, sizeof(float) * st);
+        orc_dehomogenize(f, half_w, half_h);
+        alive[i] = 1;
+    }
+    int64_t nfrag = 0, off = 0;
+    for (int64_t i = 0; i < n_points; ++i) {
+        if (!alive[i]) continue;
+        nfrag++;
+        const float *f = frag + (size_t)st * i;
+        if (f[2] < 0) continue;
+        int32_t px = orc_f2i(f[0]), py = orc_f2i(f[1]);
+        if (px < 0 || px >= W || py < 0 || py >= H) { off++; continue; }
+        uint32_t *d = depth + (size_t)py * W + px;
+        if (orc_bits(f[2]) < *d) *d = orc_bits(f[2]);
+    }
+    uint32_t *sel = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)W * H);
+    memset(sel, 0xFF, sizeof(uint32_t) * (size_t)W * H);
+    for (int64_t i = 0; i < n_points; ++i) {
+        if (!alive[i]) continue;
+        const float *f = frag + (size_t)st * i;
+        if (f[2] < 0) continue;
+        int32_t px = orc_f2i(f[0]), py = orc_f2i(f[1]);
+        if (px < 0 || px >= W || py < 0 || py >= H) continue;
+        size_t p = (size_t)py * W + px;
+        if (depth[p] == orc_bits(f[2]) && (uint32_t)i < sel[p]) sel[p] = (uint32_t)i;
+    }
+    int64_t written = 0;
+    for (size_t p = 0; p < (size_t)W * H; ++p) {
+        if (sel[p] == ORC_NO_WINNER) continue;
+        const float *f = frag + (size_t)st * sel[p];
+        float color[4];
+        orc_fragment_shader(cfg, f, color);
+        if (winner) winner[p] = sel[p];
+        if (f[2] <= 0) continue;
+        orc_pack_bgra(color, bgra + 4 * p);
+        written++;
+    }
+    S.primitives = nfrag; S.fragments = nfrag; S.fragments_offscreen = off; S.pixels_written = written;
+    free(vb); free(frag); free(alive); free(sel);
+    if (stats) *stats = S;
+    return 0;
+}
+
 /* Single-vertex known-answer helper: clip-space H and the dehomogenized proj */
 void orc_vertex_kat(const float P[3], const float *globals, int W, int H, float clip[4], float screen[4])
 {

@@ -633,6 +633,53 @@ __global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
     }
 }
 
+// ---- Raster.draw_points (rendering/_raster.py:399-414) -------------------------------------------------------------
+// One thread per point: vertex shader, PointAssembly's z<0 cull (:146), PointRaster's clip-space |x|,|y| <= w test
+// (:221), Dehomogenize, DepthTest as a 64-bit atomicMin on (depth bits, point id); a 32 B record per point keeps the
+// vertex output for the resolve pass.
+template <int SHADER>
+__global__ void __launch_bounds__(256) points_kernel(const DrawArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_tris) return; // n_tris carries the point count here
+    const long long vi = a.idx ? (long long)a.idx[i] : i;
+    VO v = vertex_shader<SHADER>(__ldg(a.pos + vi), __ldg(a.nrm + vi), a.g);
+    if (v.z < 0) return;
+    if (v.x < -v.w || v.x > v.w || v.y < -v.w || v.y > v.w) return;
+    dehomogenize(v, a.half_w, a.half_h);
+    a.rec[2 * i] = make_float4(v.x, v.y, v.z, v.w);
+    a.rec[2 * i + 1] = make_float4(v.a0, v.a1, v.a2, 0.0f);
+    if (v.z < 0) return;
+    const int ix = (int)v.x, iy = (int)v.y;
+    if (ix < 0 || ix >= a.width || iy < 0 || iy >= a.height) return;
+    atomicMin(a.key + (size_t)iy * a.width + ix, ((unsigned long long)__float_as_uint(v.z) << 32) | (unsigned)i);
+}
+
+template <int SHADER>
+__global__ void __launch_bounds__(256) resolve_points_kernel(const ResolveArgs a)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)a.width * a.height) return;
+    const unsigned long long k64 = a.key[p];
+    const unsigned prim = (unsigned)k64;
+    if (prim == RT_NO_PRIMITIVE) {
+        if (a.clear) a.bgra[p] = a.clear_px;
+        return;
+    }
+    const float4 at = __ldg(a.rec + 2 * (size_t)prim + 1);
+    float4 color;
+    if (SHADER == RT_SHADER_LESSON08) {
+        color = make_float4(at.x, at.x, at.x, 1.0f);
+    } else {
+        float4 tx = rt_sample2d(a.tex, a.tex_w, a.tex_h, at.y, at.z);
+        color = make_float4(tx.x * at.x, tx.y * at.x, tx.z * at.x, 1.0f);
+    }
+    const float z = __uint_as_float((uint32_t)(k64 >> 32));
+    if (!(z <= 0)) a.bgra[p] = rt_pack_bgra(color.x, color.y, color.z, color.w);
+    else if (a.clear) a.bgra[p] = a.clear_px;
+    a.key[p] = k64 | 0xFFFFFFFFull;
+}
+
 // ---- clears and depth views -----------------------------------------------------------------------
 
 __global__ void fill_u64_kernel(ulonglong2 *dst, long long n2, unsigned long long v, unsigned long long *tail, int ntail)
@@ -815,6 +862,50 @@ int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32
         return launch_draw<RT_SHADER_LESSON09>(da, ra, d_scratch, scratch_bytes, (cudaStream_t)stream);
     }
     return launch_draw<RT_SHADER_LESSON08>(da, ra, d_scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+int64_t rt_raster_points_scratch_bytes(int64_t n_points) { return (int64_t)CTL_BYTES + 32 * n_points; }
+
+int rt_raster_draw_points(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_points, int shader,
+                          const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_scratch,
+                          int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth, uint32_t clear_depth_bits,
+                          void *stream)
+{
+    RT_REQUIRE(n_points >= 0 && n_points < 0xFFFFFFFFll, "point count (ids are 32-bit)");
+    RT_REQUIRE(n_points == 0 || (d_pos4 && d_nrm4), "vertex arrays");
+    RT_REQUIRE(vs_globals && d_key && d_bgra && d_scratch, "globals / targets / scratch");
+    RT_REQUIRE(scratch_bytes >= rt_raster_points_scratch_bytes(n_points), "scratch buffer too small: see rt_raster_points_scratch_bytes");
+    RT_REQUIRE(width > 0 && height > 0 && width <= 32768 && height <= 32768, "viewport");
+    RT_REQUIRE(shader == RT_SHADER_LESSON08 || shader == RT_SHADER_LESSON09, "shader id");
+    cudaStream_t st = (cudaStream_t)stream;
+    DrawArgs da;
+    da.pos = (const float4 *)d_pos4; da.nrm = (const float4 *)d_nrm4; da.idx = d_indices; da.n_tris = n_points;
+    for (int i = 0; i < 48; ++i) da.g[i] = vs_globals[i];
+    da.width = width; da.height = height;
+    da.half_w = (float)width * 0.5f; da.half_h = (float)height * 0.5f;
+    da.key = (unsigned long long *)d_key; da.rec = (float4 *)((char *)d_scratch + CTL_BYTES);
+    ResolveArgs ra;
+    ra.ctl = (WorkCtl *)d_scratch; ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
+    ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
+    ra.clear = clear_rgba ? 1 : 0;
+    ra.clear_px = clear_rgba ? pack_bgra_host(clear_rgba) : 0u;
+    if (clear_depth) {
+        int rc = rt_raster_clear_depth(d_key, (int64_t)width * height, clear_depth_bits, stream);
+        if (rc != RT_OK) return rc;
+    }
+    const unsigned pblocks = (unsigned)((n_points + 255) / 256), rblocks = (unsigned)(((long long)width * height + 255) / 256);
+    if (shader == RT_SHADER_LESSON09) {
+        RT_REQUIRE(tex_handle != 0, "lesson09 shader needs a texture handle");
+        const rt_texture *t = (const rt_texture *)(uintptr_t)tex_handle;
+        ra.tex = t->obj; ra.tex_w = t->w; ra.tex_h = t->h;
+        if (n_points) points_kernel<RT_SHADER_LESSON09><<<pblocks, 256, 0, st>>>(da);
+        resolve_points_kernel<RT_SHADER_LESSON09><<<rblocks, 256, 0, st>>>(ra);
+    } else {
+        if (n_points) points_kernel<RT_SHADER_LESSON08><<<pblocks, 256, 0, st>>>(da);
+        resolve_points_kernel<RT_SHADER_LESSON08><<<rblocks, 256, 0, st>>>(ra);
+    }
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
 }
 
 int rt_texture_create(const void *d_texels, int width, int height, uint64_t *out_handle)

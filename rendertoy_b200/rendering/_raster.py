@@ -127,7 +127,29 @@ class Raster:
 
     # -- draws ------------------------------------------------------------------------------------------
     def draw_points(self, vertex_buffer, index_buffer=None):
-        raise NotImplementedError("Raster.draw_points has no native kernel yet (SURVEY.md section 8f.3)")
+        """Raster.draw_points (:399-414): one fragment per vertex (or per index), same depth / colour targets."""
+        primitive_count = vertex_buffer.shape[0] if index_buffer is None else index_buffer.shape[0]
+        pos4, nrm4 = _core.mesh_soa(vertex_buffer)
+        idx_ptr = None
+        if index_buffer is not None:
+            assert index_buffer.dtype == np.int32, "index buffer must be int32 (_raster.py:142)"
+            idx_ptr = index_buffer.ptr
+        depth_bits = self._depth_buffer.take_pending()
+        if not self._keys_armed:
+            if depth_bits is None and int(self._key_buffer.version) == 0:
+                depth_bits = 0
+            self._keys_armed = True
+        rt = self._render_target
+        need = int(_native.lib().rt_raster_points_scratch_bytes(primitive_count))
+        if self._scratch is None or self._scratch.nbytes < need:
+            self._scratch = create_buffer(need, np.uint8)
+            self._scratch_tris = -1        # forces draw_triangles to size its own layout next time
+        _native.call("rt_raster_draw_points", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
+                     self._vs_globals(), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
+                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, rt.take_pending_clear(),
+                     0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
+        self._key_buffer.device_written()
+        rt._buffer.device_written()
 
     def _vs_globals(self):
         """48 floats (World, View, Proj) as a ctypes array: the Transforms struct is three contiguous float4x4 (layout

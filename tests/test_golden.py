@@ -31,8 +31,8 @@ def test_oracle_reproduces_reference_run(oracle, path):
     depth = bgra = None
     tie = np.zeros(z["depth"].shape, np.uint8)
     for r, ix in zip(rows, idx):
-        res = oracle.draw_triangles(int(z["lesson"]), int(z["width"]), int(z["height"]), r, z["globals"], indices=ix, texture=tex,
-                                    depth=depth, bgra=bgra)
+        draw = oracle.draw_points if int(z["points"]) else oracle.draw_triangles
+        res = draw(int(z["lesson"]), int(z["width"]), int(z["height"]), r, z["globals"], indices=ix, texture=tex, depth=depth, bgra=bgra)
         depth, bgra = res.depth, res.bgra
         tie |= res.tie
     assert np.array_equal(depth, z["depth"]), "depth bits differ from the reference run"
@@ -60,7 +60,11 @@ def test_product_reproduces_reference_run(ren, path):
         vb = ren.create_buffer(r.shape[0], ren.MeshVertex)
         with ren.mapped(vb) as m:
             m.view(np.float32).reshape(r.shape)[:] = r
-        raster.draw_triangles(vb, None if ix is None else ren.create_buffer_from(np.ascontiguousarray(ix, np.int32)))
+        ib = None if ix is None else ren.create_buffer_from(np.ascontiguousarray(ix, np.int32))
+        if int(z["points"]):
+            raster.draw_points(vb, ib)
+        else:
+            raster.draw_triangles(vb, ib)
     depth = raster.get_depth_buffer().get().reshape(h, w)
     assert np.array_equal(depth, z["depth"]), "depth bits differ from the reference run"
     diff = (raster.get_render_target().get() != z["bgra"]).any(axis=-1)

@@ -82,3 +82,32 @@ def test_deferred_clears_are_not_observable(ren, oracle):
     # a second draw without clears composes on top (nothing pending any more)
     raster.draw_triangles(vb, None)
     assert np.array_equal(target.get(), res.bgra)
+
+
+@pytest.mark.parametrize("lesson,indexed", [(8, False), (9, False), (8, True)])
+def test_draw_points_matches_oracle(ren, oracle, lesson, indexed):
+    w, h = 320, 240
+    rows = scenes.dragon(3000)
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    pres = ren.create_presenter(w, h)
+    tex = texf = None
+    if lesson == 8:
+        raster, g = lessons.build_lesson08(ren, pres.get_render_target())
+    else:
+        tex = _texture()
+        raster, g, _, _ = lessons.build_lesson09(ren, pres.get_render_target(), tex)
+        texf = np.ones((tex.shape[0], tex.shape[1], 4), np.float32)
+        texf[:, :, 0:3] = tex / 255.0
+    idx = np.random.default_rng(4).integers(0, rows.shape[0], 5000).astype(np.int32) if indexed else None
+    lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8, 0.5, w, h))
+    ren.clear(raster.get_render_target())
+    ren.clear(raster.get_depth_buffer(), 1.0)
+    raster.draw_points(vb, None if idx is None else ren.create_buffer_from(idx))
+    res = oracle.draw_points(lesson, w, h, rows, lessons.globals_as_floats(g), indices=idx, texture=texf)
+    _compare(raster, res, f"points lesson{lesson:02d} indexed={indexed}")
+    # points and triangles compose on the same targets
+    raster.draw_triangles(vb, None)
+    res2 = oracle.draw_triangles(lesson, w, h, rows, lessons.globals_as_floats(g), texture=texf, depth=res.depth, bgra=res.bgra)
+    _compare(raster, res2, "points then triangles")

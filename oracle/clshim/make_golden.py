@@ -163,6 +163,81 @@ def run_lesson06_splat(out_dir):
     return 0, 0
 
 
+CUSTOM_SHADERS = '''
+@ren.kernel_struct
+class CustomTransforms:
+    WorldViewProj: ren.float4x4
+    Tint: ren.float4
+
+@ren.kernel_struct
+class CustomMaterial:
+    DiffuseMap: ren.Texture2D
+    Ambient: np.float32
+
+@ren.kernel_struct
+class CustomVertexOut:
+    proj: ren.float4
+    uv: ren.float2
+    shade: np.float32
+    tint: ren.float3
+
+@ren.kernel_function
+def custom_vs(vertex: ren.MeshVertex, info: CustomTransforms) -> CustomVertexOut:
+    """
+    CustomVertexOut o;
+    o.proj = mul((float4)(vertex.P, 1.0f), info.WorldViewProj);
+    o.uv = vertex.C * 3.0f;
+    o.shade = max(0.0f, dot(vertex.N, normalize((float3)(0.3f, 1.0f, 0.5f))));
+    o.tint = info.Tint.xyz * (vertex.P * 0.5f + 0.5f);
+    return o;
+    """
+
+@ren.kernel_function
+def custom_fs(fragment: CustomVertexOut, info: CustomMaterial) -> ren.float4:
+    """
+    float3 texel = sample2D(info.DiffuseMap, fragment.uv).xyz;
+    float3 c = texel * (info.Ambient + fragment.shade) * fragment.tint;
+    return (float4)(c, 1.0f);
+    """
+'''
+
+
+def run_custom(out_dir):
+    """A user-written shader pair (custom structs, UVs from the mesh, a tinted textured Lambert) through the
+    reference's Raster: the golden for our NVRTC-compiled general raster path."""
+    ns = {"ren": ren, "np": np}
+    exec(CUSTOM_SHADERS, ns)
+    w, h = 150, 110
+    rng = np.random.default_rng(11)
+    tex = rng.integers(0, 256, size=(19, 13, 3), dtype=np.uint8)
+    rows = scenes.dragon(1600)
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    mem, desc = ren.create_texture2D(13, 19)
+    with ren.mapped(mem) as m:
+        m = m.view(np.float32).ravel().reshape(19, 13, 4)
+        m[:, :, 0:3] = tex / 255.0
+        m[:, :, 3] = 1.0
+        texf = np.array(m)
+    g, fg = ren.create_struct(ns["CustomTransforms"]), ren.create_struct(ns["CustomMaterial"])
+    raster = ren.Raster(target, ns["custom_vs"], g, ns["custom_fs"], fg)
+    W, V, P = hm.rotate(0.8, (0, 1, 0)), hm.look_at((0, 0.3, 1.0), (0, 0, 0), (0, 1, 0)), hm.perspective(aspect_ratio=w / h)
+    wvp = hm.matmul(hm.matmul(W, V), P)
+    tint = np.array([0.9, 0.8, 1.0, 1.0], np.float32)
+    with ren.mapped(g) as m:
+        m["WorldViewProj"] = ren.make_float4x4(np.ascontiguousarray(wvp, np.float32))
+        m["Tint"] = ren.make_float4(tint)
+    with ren.mapped(fg) as m:
+        m["DiffuseMap"] = desc.get()
+        m["Ambient"] = 0.25
+    ren.clear(raster.get_render_target())
+    ren.clear(raster.get_depth_buffer(), 1.0)
+    raster.draw_triangles(upload_mesh(rows), None)
+    depth, bgra = read_targets(raster, target)
+    print(f"custom_shaders: covered={int((depth != 0x3F800000).sum())} of {w * h}")
+    np.savez_compressed(os.path.join(out_dir, "custom_shaders.npz"), rows=rows, width=w, height=h, wvp=wvp.astype(np.float32), tint=tint,
+                        ambient=np.float32(0.25), texture_rgb=tex, depth=depth, bgra=bgra, shaders=CUSTOM_SHADERS)
+
+
 def cases():
     rng = np.random.default_rng(7)
     tex = rng.integers(0, 256, size=(17, 23, 3), dtype=np.uint8)
@@ -202,10 +277,13 @@ def main():
         if sys.argv[2] == "dsl_lesson06":
             run_lesson06_splat(out_dir)
             return 0
+        if sys.argv[2] == "custom_shaders":
+            run_custom(out_dir)
+            return 0
         r = run_case(sys.argv[2], out_dir=out_dir, **cases()[sys.argv[2]])
         return 0 if r is None or (r[0] == 0 and r[1] == 0) else 1
     import subprocess
-    bad = [n for n in list(cases()) + ["dsl_lesson06"] if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
+    bad = [n for n in list(cases()) + ["dsl_lesson06", "custom_shaders"] if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
     print("ORACLE PINNED: every depth word and every non-tie colour matches the reference run" if not bad else f"MISMATCH in {bad}")
     return 0 if not bad else 1
 

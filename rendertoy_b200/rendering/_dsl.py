@@ -108,6 +108,41 @@ def compile_program(source):
     return _MODULES[key]
 
 
+def launch(module, kernel_name, n_threads, values):
+    """Launch a kernel of a compiled module.  values: ctypes objects (pointers / structures) or numpy values / arrays
+    (passed by value, byte for byte); the trailing `int number_of_threads` is appended here."""
+    keep, slots = [], (ctypes.c_void_p * (len(values) + 1))()
+    for i, v in enumerate(values):
+        if not isinstance(v, (ctypes._SimpleCData, ctypes.Structure, ctypes.Array)):
+            raw = np.ascontiguousarray(v).reshape(-1).view(np.uint8).copy()
+            keep.append(raw)
+            v = (ctypes.c_uint8 * max(raw.size, 1)).from_buffer(raw)
+        keep.append(v)
+        slots[i] = ctypes.cast(ctypes.pointer(v), ctypes.c_void_p)
+    n = ctypes.c_int(int(n_threads))
+    slots[len(values)] = ctypes.cast(ctypes.pointer(n), ctypes.c_void_p)
+    _native.call("rt_dsl_launch", module, kernel_name.encode(), int(n_threads), slots, _core.stream_ptr())
+
+
+def raster_program_source(vertex_shader, fragment_shader, vin, vout, vsg, fsg):
+    """Program for Raster with user shaders: prelude, structs, the shaders and what they call, raster_generic.cuh."""
+    parts = [open(os.path.join(_HERE, "cl_prelude.cuh")).read()]
+    functions = _reachable_functions(f"{vertex_shader.name}( {fragment_shader.name}(")
+    if any("sample2D" in f.source for f in functions):
+        parts.append(f"__device__ const unsigned long long memory_pool_ptr = {_core.__MEMORY_POOL__.get_buffer().ptr}ull;\n"
+                     "#define sample2D(texture, c) cl_sample2D(memory_pool_ptr, (texture), (c))\n")
+    for name, dt in _core._STRUCTS.items():
+        fields = "\n".join(f"    {_core.dtype_cname(dt.fields[n][0])} {n};" for n in dt.names)
+        parts.append(f"struct {name} {{\n{fields}\n}};\nstatic_assert(sizeof({name}) == {dt.itemsize}, \"{name}: layout differs from the host dtype\");\n")
+    for f in functions:
+        sig = ", ".join(f"{_ctype(p.annotation)} {p.name}" for _, p in f.signature)
+        parts.append(f"__device__ {_ctype(f.return_annotation)} {f.name}({sig}) {{\n{to_cuda(f.source)}\n}}\n")
+    parts.append(f"#define VIN_T {_ctype(vin)}\n#define VOUT_T {_ctype(vout)}\n#define VSG_T {_ctype(vsg)}\n#define FSG_T {_ctype(fsg)}\n"
+                 f"#define VS_FN {vertex_shader.name}\n#define FS_FN {fragment_shader.name}\n")
+    parts.append(open(os.path.join(_HERE, "raster_generic.cuh")).read())
+    return "\n".join(parts)
+
+
 class Dispatcher:
     """`kernel[n](*args)` (rendering/_core.py:261-290)."""
 

@@ -16,6 +16,7 @@ Same constructor, same methods, same assertion messages.  What is behind them di
 Results are bit-identical to the oracle's restatement of the reference pipeline (depth bits, winners, BGRA8).
 """
 import hashlib
+import os
 import re
 from enum import IntEnum
 
@@ -84,7 +85,8 @@ class Raster:
         self.vertex_shader_globals = vertex_shader_globals
         self.fragment_shader_globals = fragment_shader_globals
 
-        self.shader_id = self._resolve_builtin()
+        self.shader_id = self._resolve_builtin()     # None -> user shaders: NVRTC-compiled generic pipeline
+        self._generic = None if self.shader_id is not None else self._build_generic()
         self._scratch = None
         self._scratch_tris = -1
         # kept for API compatibility with code that reads them (:378-380); nothing is sized by them here
@@ -95,20 +97,72 @@ class Raster:
     def _resolve_builtin(self):
         key = (shader_fingerprint(self.vertex_shader.source), shader_fingerprint(self.fragment_shader.source))
         sid = _BUILTIN_SHADERS.get(key)
-        if sid is None:
-            raise NotImplementedError(
-                f"Raster: shader pair ({self.vertex_shader.name}, {self.fragment_shader.name}) is not one of the "
-                "built-in tutorial pairs; custom OpenCL-C shaders need the NVRTC path (not available yet). "
-                "There is no CPU fallback.")
+        if sid is None or os.environ.get("RENDERTOY_B200_GENERIC_RASTER") == "1":
+            return None
         f4, f3, f2, m4 = _core.float4, _core.float3, _core.float2, _core.float4x4
-        _check_layout(self.vertex_input_type, [(f3, 0), (f3, 16), (f2, 32), (f3, 48), (f3, 64)], "vertex input")
-        _check_layout(self.vertex_globals_type, [(m4, 0), (m4, 64), (m4, 128)], "vertex globals")
-        if sid == _native.SHADER_LESSON08:
-            _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16)], "vertex output")
-        else:
-            _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16), (f2, 32)], "vertex output")
-            _check_layout(self.fragment_globals_type, [(_core.Texture2D, 0)], "fragment globals")
+        try:
+            _check_layout(self.vertex_input_type, [(f3, 0), (f3, 16), (f2, 32), (f3, 48), (f3, 64)], "vertex input")
+            _check_layout(self.vertex_globals_type, [(m4, 0), (m4, 64), (m4, 128)], "vertex globals")
+            if sid == _native.SHADER_LESSON08:
+                _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16)], "vertex output")
+            else:
+                _check_layout(self.vertex_output_type, [(f4, 0), (f3, 16), (f2, 32)], "vertex output")
+                _check_layout(self.fragment_globals_type, [(_core.Texture2D, 0)], "fragment globals")
+        except NotImplementedError:
+            return None       # same shader text over different struct layouts: take the general path
         return sid
+
+    def _build_generic(self):
+        """User shaders: compile the general pipeline (rendering/raster_generic.cuh) around them with NVRTC."""
+        from . import _dsl
+        vout = np.dtype(self.vertex_output_type)
+        first = vout.names[0]
+        assert vout.fields[first][1] == 0 and vout.fields[first][0] == _core.float4, \
+            "the first field of the vertex shader's output must be the float4 projected position"
+
+        def all_float(dt):
+            dt = np.dtype(dt)
+            return all(all_float(dt.fields[n][0]) for n in dt.names) if dt.names else dt == np.float32
+        assert all_float(vout), "every field of the vertex shader's output must be made of floats (they are interpolated)"
+        src = _dsl.raster_program_source(self.vertex_shader, self.fragment_shader, self.vertex_input_type, vout,
+                                         self.vertex_globals_type, self.fragment_globals_type)
+        return {"module": _dsl.compile_program(src), "nf": vout.itemsize // 4, "dsl": _dsl, "rec": None}
+
+    def _generic_draw(self, vertex_buffer, index_buffer, points):
+        import ctypes
+        g, rt = self._generic, self._render_target
+        count = vertex_buffer.shape[0] if index_buffer is None else index_buffer.shape[0]
+        n = count if points else count // 3
+        assert vertex_buffer.dtype.itemsize == np.dtype(self.vertex_input_type).itemsize, "vertex buffer type differs from the vertex shader's input"
+        rec_floats = n * g["nf"] * (1 if points else 6)
+        if g["rec"] is None or g["rec"].size < rec_floats:
+            g["rec"] = create_buffer(max(rec_floats, 4), np.float32)
+        depth_bits = self._depth_buffer.take_pending()
+        if not self._keys_armed:
+            if depth_bits is None and int(self._key_buffer.version) == 0:
+                depth_bits = 0
+            self._keys_armed = True
+        if depth_bits is not None:
+            self._depth_buffer.fill(depth_bits)
+        clear = rt.take_pending_clear()
+        clear_px = 0
+        if clear is not None:
+            v = np.clip(np.array([clear[2], clear[1], clear[0], clear[3]], np.float32) * np.float32(255.0), 0, 255)
+            b = np.rint(v).astype(np.uint32)
+            clear_px = int(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24))
+        P = ctypes.c_void_p
+        ib = P(index_buffer.ptr) if index_buffer is not None else P(0)
+        if index_buffer is not None:
+            assert index_buffer.dtype == np.int32, "index buffer must be int32"
+        W, H = np.int32(rt.width), np.int32(rt.height)
+        kind = "points" if points else "triangles"
+        g["dsl"].launch(g["module"], f"g_raster_{kind}", n,
+                        [P(vertex_buffer.ptr), ib, self.vertex_shader_globals.get(), P(self._key_buffer.ptr), P(g["rec"].ptr), W, H])
+        g["dsl"].launch(g["module"], f"g_resolve_{kind}", rt.width * rt.height,
+                        [P(self._key_buffer.ptr), P(g["rec"].ptr), self.fragment_shader_globals.get(), P(rt.raw_ptr), W, H,
+                         np.int32(0 if clear is None else 1), np.uint32(clear_px)])
+        self._key_buffer.device_written()
+        rt._buffer.device_written()
 
     # -- reference accessors (:385-397) ---------------------------------------------------------------
     def get_render_target(self):
@@ -128,6 +182,8 @@ class Raster:
     # -- draws ------------------------------------------------------------------------------------------
     def draw_points(self, vertex_buffer, index_buffer=None):
         """Raster.draw_points (:399-414): one fragment per vertex (or per index), same depth / colour targets."""
+        if self._generic is not None:
+            return self._generic_draw(vertex_buffer, index_buffer, points=True)
         primitive_count = vertex_buffer.shape[0] if index_buffer is None else index_buffer.shape[0]
         pos4, nrm4 = _core.mesh_soa(vertex_buffer)
         idx_ptr = None
@@ -166,6 +222,8 @@ class Raster:
     def draw_triangles(self, vertex_buffer, index_buffer):
         """Raster.draw_triangles (:416-437).  index_buffer None -> triangle soup; else int32 indices.
         Accumulates into the persistent depth / colour targets exactly like consecutive reference draws."""
+        if self._generic is not None:
+            return self._generic_draw(vertex_buffer, index_buffer, points=False)
         primitive_count = (vertex_buffer.shape[0] if index_buffer is None else index_buffer.shape[0]) // 3
         pos4, nrm4 = _core.mesh_soa(vertex_buffer)
         idx_ptr = None

@@ -152,8 +152,18 @@ def test_raster_recognises_tutorial_shaders_and_rejects_others(ren):
         return (float4)(fragment.C, 1);
         """
 
-    with pytest.raises(NotImplementedError):
-        ren.Raster(pres.get_render_target(), vs, ren.create_struct(ren.float4x4), fs, ren.create_struct(ren.float4x4))
+    # a user-written pair is compiled with NVRTC around the general pipeline (works without a GPU; drawing needs one)
+    custom = ren.Raster(pres.get_render_target(), vs, ren.create_struct(ren.float4x4), fs, ren.create_struct(ren.float4x4))
+    assert custom.shader_id is None and custom._generic["nf"] == 8
+
+    @ren.kernel_function
+    def broken_fs(fragment: VOut, info: ren.float4x4) -> ren.float4:
+        """
+        return not_a_function(fragment.C);
+        """
+
+    with pytest.raises(RuntimeError, match="failed to build"):
+        ren.Raster(pres.get_render_target(), vs, ren.create_struct(ren.float4x4), broken_fs, ren.create_struct(ren.float4x4))
     with pytest.raises(AssertionError, match="Fragment shader signature incorrect"):
         ren.Raster(pres.get_render_target(), vs, None, vs, None)
     with pytest.raises(Exception, match="Can not call to this function from host"):

@@ -163,8 +163,11 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
     const long long n_units = MODE ? (long long)tiles_x * ((a.h + 3) >> 2) : (a.n_rays + 31) >> 5;
     const float two_over_w = MODE ? 2.0f / (float)a.width : 0.0f, two_over_h = MODE ? 2.0f / (float)a.height : 0.0f;
 
-    // (claiming the next unit early to hide the atomic's L2 round trip measured 6 % SLOWER on B200, and carrying entry
-    //  distances on the stack to drop stale subtrees at pop time 10 % slower: neither is done)
+    // Measured on B200 and NOT adopted (4K frame, dragon100k, 322 us with this loop): claiming the next tile early (+6 %),
+    // claiming 8 tiles per atomic (+65 %: the tail grows), entry distances on the stack for pop-time culling (+10 %),
+    // per-lane refill a la Aila-Laine, idle lanes claiming single pixels (+27 %: primary rays are coherent, mixing tiles in
+    // a warp costs more in divergent node fetches than parked lanes do).  The stall samples ncu books on this atomic are
+    // lanes waiting at the reconvergence point for the longest ray of their tile.
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(a.ctl, 1u);

@@ -317,6 +317,82 @@ __device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned p
     cover_cell(e, col, row, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, __float_as_uint(s3.y), key, W, H);
 }
 
+// Coverage of the primitives staged in `my_slots` (compacted, owner lane i holds ny / off of slot i): their rows are
+// laid end to end and taken 32 at a time, one row per lane.  A lane finds the exact interval of its row that the
+// division-free sign test accepts (the float edge functions are monotone in px, so per edge the accepted cells are a
+// half-line: an analytic guess is corrected by evaluating the real predicate), pushes those cells on the warp's
+// candidate stack, and full warps of candidates go through the exact test + depth atomics.
+__device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ring, int ny, int off, int total, int lane,
+                                           unsigned long long *key, int W, int H)
+{
+    const unsigned FULL = 0xffffffffu, le_mask = (2u << lane) - 1u;
+    int started = 0; // compacted primitives whose first row lies before `base`
+    int pending = 0; // candidates on the stack (warp-uniform, < 32 between passes)
+    for (int base = 0; base < total; base += 32) {
+        const unsigned rel = (unsigned)(off - base);
+        const unsigned starts = __reduce_or_sync(FULL, (ny > 0 && rel < 32u) ? (1u << rel) : 0u);
+        const int slot = started + __popc(starts & le_mask) - 1;
+        started += __popc(starts);
+        int lo = 0, hi = -1, lrow = 0;
+        if (base + lane < total) {
+            const float4 *sp = reinterpret_cast<const float4 *>(my_slots + slot);
+            const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+            const int nx_tle = __float_as_int(sp[3].x), sxy = __float_as_int(s2.w);
+            lrow = base + lane - __float_as_int(s2.z);
+            hi = (nx_tle & 0xffff) - 1;
+            if (nx_tle & (1 << 19)) { // sign(s) is one constant over the bbox: exact spans
+                const float sg = (nx_tle & (1 << 20)) ? -1.0f : 1.0f;
+                const float x0 = (float)(sxy & 0xffff) + 0.5f; // px of local column 0
+                const float py = (float)((sxy >> 16) + lrow) + 0.5f;
+                const float ea[3] = {s0.x, s0.w, s1.z}, eb[3] = {s0.y, s1.x, s1.w}, ec[3] = {s0.z, s1.y, s2.x};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float ak = ea[k], tk = eb[k] * py, ck = ec[k];
+                    // accepted(col) <=> !(sg * ((ak * px + tk) + ck) < 0), px = x0 + col  (same expression as cell_eval)
+                    const float dir = sg * ak;
+                    if (dir > 0.0f) {        // accepted for col >= L
+                        int L = __float2int_ru(__fdividef(-(tk + ck), ak) - x0);
+                        L = min(max(L, lo), hi + 1);
+                        while (L > lo && !(sg * ((ak * (x0 + (float)(L - 1)) + tk) + ck) < 0.0f)) --L;
+                        while (L <= hi && (sg * ((ak * (x0 + (float)L) + tk) + ck) < 0.0f)) ++L;
+                        lo = L;
+                    } else if (dir < 0.0f) { // accepted for col <= U
+                        int U = __float2int_rd(__fdividef(-(tk + ck), ak) - x0);
+                        U = min(max(U, lo - 1), hi);
+                        while (U < hi && !(sg * ((ak * (x0 + (float)(U + 1)) + tk) + ck) < 0.0f)) ++U;
+                        while (U >= lo && (sg * ((ak * (x0 + (float)U) + tk) + ck) < 0.0f)) --U;
+                        hi = U;
+                    } else if (sg * ((ak * x0 + tk) + ck) < 0.0f) { // constant along the row (ak == 0 or NaN): all or nothing
+                        hi = lo - 1;
+                    }
+                }
+            }
+        }
+        // push the spans, at most 4 cells per lane per pass, and drain full warps of candidates
+        int remaining = hi >= lo ? hi - lo + 1 : 0;
+        while (__any_sync(FULL, remaining > 0)) {
+            const int n = min(remaining, 4);
+            int pin = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(FULL, pin, d);
+                if (lane >= d) pin += v;
+            }
+            const int ptot = __shfl_sync(FULL, pin, 31);
+            const unsigned head = ((unsigned)slot << 24) | ((unsigned)lrow << 12);
+            for (int j = 0; j < n; ++j) my_ring[pending + pin - n + j] = head | (unsigned)(lo + j);
+            lo += n; remaining -= n; pending += ptot;
+            __syncwarp();
+            while (pending >= 32) {
+                pending -= 32;
+                cover_from_slot(my_slots, my_ring[pending + lane], key, W, H);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane < pending) cover_from_slot(my_slots, my_ring[lane], key, W, H);
+}
+
 template <int SHADER>
 __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
 {
@@ -392,71 +468,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
         }
         __syncwarp();
 
-        int started = 0; // compacted primitives whose first row lies before `base`
-        int pending = 0; // candidates on the stack (warp-uniform, < 32 between passes)
-        for (int base = 0; base < total; base += 32) {
-            const unsigned rel = (unsigned)(off - base);
-            const unsigned starts = __reduce_or_sync(FULL, (ny > 0 && rel < 32u) ? (1u << rel) : 0u);
-            const int slot = started + __popc(starts & le_mask) - 1;
-            started += __popc(starts);
-            int lo = 0, hi = -1, lrow = 0;
-            if (base + lane < total) {
-                const float4 *sp = reinterpret_cast<const float4 *>(my_slots + slot);
-                const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2];
-                const int nx_tle = __float_as_int(sp[3].x), sxy = __float_as_int(s2.w);
-                lrow = base + lane - __float_as_int(s2.z);
-                hi = (nx_tle & 0xffff) - 1;
-                if (nx_tle & (1 << 19)) { // sign(s) is one constant over the bbox: exact spans
-                    const float sg = (nx_tle & (1 << 20)) ? -1.0f : 1.0f;
-                    const float x0 = (float)(sxy & 0xffff) + 0.5f; // px of local column 0
-                    const float py = (float)((sxy >> 16) + lrow) + 0.5f;
-                    const float ea[3] = {s0.x, s0.w, s1.z}, eb[3] = {s0.y, s1.x, s1.w}, ec[3] = {s0.z, s1.y, s2.x};
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float ak = ea[k], tk = eb[k] * py, ck = ec[k];
-                        // accepted(col) <=> !(sg * ((ak * px + tk) + ck) < 0), px = x0 + col  (same expression as cell_eval)
-                        const float dir = sg * ak;
-                        if (dir > 0.0f) {        // accepted for col >= L
-                            int L = __float2int_ru(__fdividef(-(tk + ck), ak) - x0);
-                            L = min(max(L, lo), hi + 1);
-                            while (L > lo && !(sg * ((ak * (x0 + (float)(L - 1)) + tk) + ck) < 0.0f)) --L;
-                            while (L <= hi && (sg * ((ak * (x0 + (float)L) + tk) + ck) < 0.0f)) ++L;
-                            lo = L;
-                        } else if (dir < 0.0f) { // accepted for col <= U
-                            int U = __float2int_rd(__fdividef(-(tk + ck), ak) - x0);
-                            U = min(max(U, lo - 1), hi);
-                            while (U < hi && !(sg * ((ak * (x0 + (float)(U + 1)) + tk) + ck) < 0.0f)) ++U;
-                            while (U >= lo && (sg * ((ak * (x0 + (float)U) + tk) + ck) < 0.0f)) --U;
-                            hi = U;
-                        } else if (sg * ((ak * x0 + tk) + ck) < 0.0f) { // constant along the row (ak == 0 or NaN): all or nothing
-                            hi = lo - 1;
-                        }
-                    }
-                }
-            }
-            // push the spans, at most 4 cells per lane per pass, and drain full warps of candidates
-            int remaining = hi >= lo ? hi - lo + 1 : 0;
-            while (__any_sync(FULL, remaining > 0)) {
-                const int n = min(remaining, 4);
-                int pin = n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int v = __shfl_up_sync(FULL, pin, d);
-                    if (lane >= d) pin += v;
-                }
-                const int ptot = __shfl_sync(FULL, pin, 31);
-                const unsigned head = ((unsigned)slot << 24) | ((unsigned)lrow << 12);
-                for (int j = 0; j < n; ++j) my_ring[pending + pin - n + j] = head | (unsigned)(lo + j);
-                lo += n; remaining -= n; pending += ptot;
-                __syncwarp();
-                while (pending >= 32) {
-                    pending -= 32;
-                    cover_from_slot(my_slots, my_ring[pending + lane], a.key, W, H);
-                }
-                __syncwarp();
-            }
-        }
-        if (lane < pending) cover_from_slot(my_slots, my_ring[lane], a.key, W, H);
+        cover_rows(my_slots, my_ring, ny, off, total, lane, a.key, W, H);
     }
 }
 
@@ -625,6 +637,9 @@ __global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
         const int y = y0 + 4 * i;
         k[i] = y < a.height ? __ldcs(a.key + (size_t)y * a.width + x) : ~0ull;
     }
+    // Measured on B200 and NOT adopted (dragon100k, 1080p, frame 96.0 us with this form): 1 or 2 pixels per thread and/or 4-6
+    // resident blocks per SM via __launch_bounds__ (64 / 48 / 40 registers): 96.5-114 us -- the register caps spill, and
+    // fewer pixels per thread lose the memory-level parallelism of the four up-front key loads.
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const unsigned long long k64 = i == 0 ? k[0] : i == 1 ? k[1] : i == 2 ? k[2] : k[3];

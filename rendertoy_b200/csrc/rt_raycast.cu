@@ -166,8 +166,10 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
     // Measured on B200 and NOT adopted (4K frame, dragon100k, 322 us with this loop): claiming the next tile early (+6 %),
     // claiming 8 tiles per atomic (+65 %: the tail grows), entry distances on the stack for pop-time culling (+10 %),
     // per-lane refill a la Aila-Laine, idle lanes claiming single pixels (+27 %: primary rays are coherent, mixing tiles in
-    // a warp costs more in divergent node fetches than parked lanes do).  The stall samples ncu books on this atomic are
-    // lanes waiting at the reconvergence point for the longest ray of their tile.
+    // a warp costs more in divergent node fetches than parked lanes do), a warp-synchronous while-while loop that parks leaves
+    // and runs node steps and triangle tests in separate ballot-driven phases (+44 %: lanes blocked on two parked leaves wait
+    // for the deepest lane of every phase), 12 instead of 10 resident blocks per SM via __launch_bounds__ (40 registers, +-0 %).
+    // The stall samples ncu books on this atomic are lanes waiting at the reconvergence point for the longest ray of their tile.
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(a.ctl, 1u);

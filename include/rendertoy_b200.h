@@ -121,9 +121,9 @@ int rt_bvh_build(const void *d_pos4, const int32_t *d_indices, int64_t n_triangl
                  void *d_scratch, void *stream);
 /* Raycaster.ray_cast (rendering/_raycaster.py:35-36): rays = n x {float3 origin, float3 dir} (32 B, OpenCL
  * float3 padding), hits = n x {float t, uint32 triangle, float u, float v} (16 B); miss: t = +inf,
- * triangle = 0xFFFFFFFF.  d_ctl: 256-byte control block, ZERO-FILLED once by the caller (the kernel re-arms it). */
+ * triangle = 0xFFFFFFFF. */
 int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_rays, int64_t n_rays,
-                    void *d_hits, void *d_ctl, void *stream);
+                    void *d_hits, void *stream);
 /* Fused primary-ray generation + closest hit + Lambert/texture shade for the pixel rect
  * [x0,x0+w) x [y0,y0+h) of a width x height frame.  camera = {origin, U, V, W} (12 floats, model space,
  * HOST memory): dir = (U*sx + V*sy) + W with (sx, sy) the NDC pixel centre.  Outputs are rect-local,
@@ -133,11 +133,17 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * build of the kernel ADDS {inner-node visits, triangle tests, rays} to (for the roofline report; slower).
  * cull_rect: NULL, or 4 ints {x0, y0, x1, y1} (inclusive, frame pixels): a conservative screen-space bound of the
  * scene the caller computed; pixels outside are written as misses without tracing.  fast_slab: non-zero lets the
- * box tests use the FMA form (caller guarantees the origin is within 16 scene extents of the scene). */
+ * box tests use the FMA form (caller guarantees the origin is within 16 scene extents of the scene).
+ * d_view_nodes: NULL, or rt_raycast_view_node_bytes(n_triangles) of 16-byte aligned device scratch: the call then
+ * first projects every BVH node into this camera's screen space (one small kernel) and the traversal tests pixels
+ * against screen rectangles instead of rays against boxes -- same hits, fewer instructions per node.  The scratch is
+ * per call: concurrent calls on different streams need different buffers. */
+int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
-                       int64_t bgra_pitch_px, void *d_ctl, void *d_stats, const int *cull_rect, int fast_slab, void *stream);
+                       int64_t bgra_pitch_px, void *d_stats, const int *cull_rect, int fast_slab,
+                       void *d_view_nodes, void *stream);
 
 /* ---- run-time kernels  (rendering/_core.py:247-299: kernel_main / build_kernel_main, one OpenCL program built at
  * first dispatch) --------------------------------------------------------------------------------------------

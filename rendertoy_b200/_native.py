@@ -31,9 +31,10 @@ SIGNATURES = {
     "rt_bvh_tri_bytes": (_I64, [_I64]),
     "rt_bvh_scratch_bytes": (_I64, [_I64]),
     "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
-    "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
+    "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP]),
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
-                                     _I64, _VP, _VP, C.POINTER(C.c_int), _I32, _VP]),
+                                     _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),
+    "rt_raycast_view_node_bytes": (_I64, [_I64]),
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),
     "rt_dsl_launch": (C.c_int, [_U64, C.c_char_p, _I64, C.POINTER(_VP), _VP]),
     "rt_dsl_unload": (C.c_int, [_U64]),

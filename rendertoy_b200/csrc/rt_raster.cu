@@ -143,20 +143,6 @@ __device__ __forceinline__ Cell cell_eval(const Edges &e, int col, int row)
     return c;
 }
 
-// Necessary condition for cell_eval(...).inside, without the three divisions: alpha_k = d_k / s is negative (and
-// fails alpha_k >= comp_k for comp_k in {0, 1e-8}) whenever d_k and s have strictly opposite signs, i.e. the
-// float product d_k * s is < 0.  Zeros, underflow and NaN make the product non-negative/unordered, so those
-// cells fall through to the exact test: the filter only ever rejects cells the exact test rejects.
-__device__ __forceinline__ bool cell_maybe_inside(const Edges &e, int col, int row)
-{
-    float px = (float)col + 0.5f, py = (float)row + 0.5f;
-    float d1 = e.a1 * px + e.b1 * py + e.c1;
-    float d2 = e.a2 * px + e.b2 * py + e.c2;
-    float d3 = e.a3 * px + e.b3 * py + e.c3;
-    float s = d1 + d2 + d3;
-    return !(d1 * s < 0.0f || d2 * s < 0.0f || d3 * s < 0.0f);
-}
-
 __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, float w2, float w3)
 {
     return f1 * w1 + f2 * w2 + f3 * w3;
@@ -400,7 +386,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
     __shared__ unsigned ring[RW][RING];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int W = a.width, H = a.height;
     Slot *my_slots = slots[wid];
     unsigned *my_ring = ring[wid];

@@ -2,9 +2,9 @@
 // semantics are those of oracle/raycast_oracle.c: float32 Moller-Trumbore without FMA, closest hit = min over
 // (bits(t) << 32 | triangle id)).
 //
-// One persistent kernel: warps pull 8x4-pixel tiles (or 32-ray groups) from an atomic counter, every lane walks
-// the LBVH with its own short stack (local memory, L1-resident), inner nodes are four 128-bit
-// read-only loads that test both children, leaves are three.  Primary mode generates the ray from the camera
+// One kernel, one warp per 8x4-pixel tile (or 32-ray group), scheduled by the hardware (see raycast_kernel for why not a
+// persistent loop); every lane walks the LBVH with its own short stack (local memory, L1-resident), inner nodes are four
+// 128-bit read-only loads that test both children (three in the per-frame screen-space form), leaves are three.  Primary mode generates the ray from the camera
 // frame in-kernel and shades the hit (Lambert / texture) straight into the BGRA8 frame, so per ray only 4 B
 // (+16 B if hits are requested) leave the SM.
 //
@@ -21,9 +21,92 @@ constexpr int STACK = 64; // Karras tree depth <= 64 (32 key bits + index tiebre
 // against a [depth][thread] shared-memory stack: 332 vs 374 us per 4K frame -- the 32 KB of shared memory per CTA
 // cost more occupancy than the L1 round trips do.
 
+// Primary rays share one origin, so a box test does not need the ray at all: with (a, b, c) the coordinates of a point in
+// the camera's (U, V, W) basis, the ray through screen point (sx, sy) passes a point iff a / c = sx and b / c = sy, and
+// its parameter there is t = c.  Once per frame project_kernel turns every inner node into the two children's screen
+// rectangles (bounding the eight projected corners, padded by the direction rounding, see project_kernel) and minimum c;
+// a node visit is then 3 loads + 10 compares instead of 4 loads + 12 FMA + 20 min/max.  The rectangle of a projected box
+// is looser than the box (more visits), the exact Moller-Trumbore test at the leaves is unchanged, so are the hits.
+struct __align__(16) ViewNode {
+    float4 r0, r1; // child 0 / child 1: (sx_min, sx_max, sy_min, sy_max)
+    float4 zc;     // (c_min child 0, c_min child 1, child0 bits, child1 bits)
+};
+
+struct ProjectArgs {
+    const RtBvhNode *nodes;
+    ViewNode *vnodes;
+    long long n_inner;
+    double minv[9]; // rows of [U V W]^-1
+    double o[3];
+    float pad_s;    // rectangle padding per unit of (1 + |s|)
+};
+
+__device__ __forceinline__ void project_child(const ProjectArgs &p, float lox, float hix, float loy, float hiy, float loz, float hiz, float4 &rect,
+                                              float &zmin)
+{
+    if (lox > hix) { // the empty box of a single-triangle scene
+        rect = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+        zmin = INFINITY;
+        return;
+    }
+    // (a, b, c) is affine in the corner: base + ix * ex + iy * ey + iz * ez
+    const double qx = (double)lox - p.o[0], qy = (double)loy - p.o[1], qz = (double)loz - p.o[2];
+    const double wx = (double)hix - (double)lox, wy = (double)hiy - (double)loy, wz = (double)hiz - (double)loz;
+    double base[3], ex[3], ey[3], ez[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        base[r] = p.minv[3 * r] * qx + p.minv[3 * r + 1] * qy + p.minv[3 * r + 2] * qz;
+        ex[r] = p.minv[3 * r] * wx; ey[r] = p.minv[3 * r + 1] * wy; ez[r] = p.minv[3 * r + 2] * wz;
+    }
+    float smin = INFINITY, smax = -INFINITY, tmin = INFINITY, tmax = -INFINITY, cmin = INFINITY, qmax = 0.0f;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double a = base[0], b = base[1], c = base[2];
+        if (k & 1) { a += ex[0]; b += ex[1]; c += ex[2]; }
+        if (k & 2) { a += ey[0]; b += ey[1]; c += ey[2]; }
+        if (k & 4) { a += ez[0]; b += ez[1]; c += ez[2]; }
+        const float af = (float)a, bf = (float)b, cf = (float)c;
+        const float s = af / cf, t = bf / cf; // float division: 2^-23 relative, far inside the padding
+        smin = fminf(smin, s); smax = fmaxf(smax, s); tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+        cmin = fminf(cmin, cf);
+        qmax = fmaxf(qmax, fmaxf(fabsf(af), fabsf(bf)));
+        bad = bad || !(fabsf(s) < INFINITY) || !(fabsf(t) < INFINITY) || !(fabsf(cf) < INFINITY);
+    }
+    // a corner at or behind the eye plane (or non-finite data): every ray may pass -- no rectangle, no depth bound
+    if (bad || !(cmin > 1e-6f * qmax) || !(cmin > 0.0f)) {
+        rect = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+        zmin = 0.0f;
+        return;
+    }
+    rect.x = smin - p.pad_s * (1.0f + fabsf(smin)); rect.y = smax + p.pad_s * (1.0f + fabsf(smax));
+    rect.z = tmin - p.pad_s * (1.0f + fabsf(tmin)); rect.w = tmax + p.pad_s * (1.0f + fabsf(tmax));
+    zmin = cmin * (1.0f - 64.0f * p.pad_s);
+}
+
+// One thread per inner node.  Padding: the traced direction is fl(fl(U sx + V sy) + W), off the exact U sx + V sy + W by
+// at most eps_d = 2^-22 (|U| |sx| + |V| |sy| + |W|) per component; through [U V W]^-1 that moves the ray's screen point by
+// <= rowsum |Minv| eps_d (1 + |s|) -- the host passes pad_s = 8 x that bound (about 3 % of a 4K pixel for the lesson
+// cameras).  The 3-D boxes already carry the 2^-17-extent padding that covers Moller-Trumbore's own rounding.
+__global__ void __launch_bounds__(128) project_kernel(const ProjectArgs p)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_inner) return;
+    const float4 *np = reinterpret_cast<const float4 *>(p.nodes + i);
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+    const int4 n3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+    ViewNode v;
+    float z0, z1;
+    project_child(p, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, v.r0, z0);
+    project_child(p, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, v.r1, z1);
+    v.zc = make_float4(z0, z1, __int_as_float(n3.x), __int_as_float(n3.y));
+    p.vnodes[i] = v;
+}
+
 struct TraceArgs {
     const RtBvhNode *nodes;
     const RtBvhTri *tris;
+    const ViewNode *vnodes;     // primary-ray mode: this frame's camera-space nodes (or null: walk the 3-D nodes)
     // primary-ray mode
     float cam[12]; // origin, U, V, W
     int width, height, x0, y0, w, h;
@@ -39,8 +122,9 @@ struct TraceArgs {
     const int *idx;
     cudaTextureObject_t tex;
     int tex_w, tex_h;
-    unsigned *ctl; // [0] next work unit, [1] finished blocks; both zero between launches
     int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
+    int tt[4];     // primary mode: traced tile rectangle {tile x0, tile y0, tiles wide, tiles high} (8x4-pixel tiles of the rect)
+    int trace_blocks; // primary mode: blocks [0, trace_blocks) trace 2x2 tiles each, the rest clear
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
 
@@ -129,6 +213,70 @@ __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, flo
     return h;
 }
 
+// trace() over this frame's ViewNodes: same stack discipline, same exact triangle test, box tests in screen space.
+template <bool STATS>
+__device__ __forceinline__ Hit trace_view(const TraceArgs &a, float sx, float sy, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          int *stack)
+{
+    unsigned long long best = ~0ull;
+    float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
+    int sp = 0, cur = 0;
+    unsigned n_nodes = 0, n_tests = 0;
+    for (;;) {
+        if (cur >= 0) {
+            if (STATS) ++n_nodes;
+            const float4 *np = reinterpret_cast<const float4 *>(a.vnodes + cur);
+            const float4 r0 = __ldg(np), r1 = __ldg(np + 1), zc = __ldg(np + 2);
+            const bool h0 = sx >= r0.x && sx <= r0.y && sy >= r0.z && sy <= r0.w && zc.x <= tbest;
+            const bool h1 = sx >= r1.x && sx <= r1.y && sy >= r1.z && sy <= r1.w && zc.y <= tbest;
+            const int c0 = __float_as_int(zc.z), c1 = __float_as_int(zc.w);
+            if (h0 && h1) {
+                const bool swap = zc.y < zc.x;
+                stack[sp] = swap ? c0 : c1;
+                ++sp;
+                cur = swap ? c1 : c0;
+                continue;
+            }
+            if (h0) { cur = c0; continue; }
+            if (h1) { cur = c1; continue; }
+        } else {
+            if (STATS) ++n_tests;
+            const float4 *tp = reinterpret_cast<const float4 *>(a.tris + ~cur);
+            const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+            // Moller-Trumbore, operation for operation as oracle/raycast_oracle.c: rc_moller_trumbore
+            const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
+            const float det = (e1.x * px + e1.y * py) + e1.z * pz;
+            if (det != 0.0f) {
+                const float inv = 1.0f / det;
+                const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
+                const float u = ((tx * px + ty * py) + tz * pz) * inv;
+                if (u >= 0.0f && !(u > 1.0f)) {
+                    const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
+                    const float v = ((dx * qx + dy * qy) + dz * qz) * inv;
+                    if (v >= 0.0f && !(u + v > 1.0f)) {
+                        const float t = ((e2.x * qx + e2.y * qy) + e2.z * qz) * inv;
+                        if (t > 0.0f && t != INFINITY) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(v0.w);
+                            if (key < best) { best = key; tbest = t; bu = u; bv = v; }
+                        }
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        cur = stack[sp];
+    }
+    if (STATS) {
+        atomicAdd(a.stats, (unsigned long long)n_nodes);
+        atomicAdd(a.stats + 1, (unsigned long long)n_tests);
+        atomicAdd(a.stats + 2, 1ull);
+    }
+    Hit h;
+    h.t = tbest; h.u = bu; h.v = bv; h.id = best == ~0ull ? 0xFFFFFFFFu : (unsigned)best;
+    return h;
+}
+
 // Lambert / texture shade of a hit, as oracle/raycast_oracle.c: orc_shade_hits
 template <int SHADER>
 __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
@@ -153,78 +301,126 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 }
 
 // MODE 0: rays from a buffer, hits out.  MODE 8 / 9: primary rays + shade with that lesson's shader.
-template <int MODE, bool STATS, bool FMA>
+//
+// One warp per work unit (an 8x4-pixel tile or 32 consecutive rays), four units per block, and the hardware block
+// scheduler as the load balancer.  The first version of this kernel was the textbook persistent-threads loop (resident
+// warps claiming tiles with atomicAdd on one counter): at 4K that is 259 200 claims per frame, and the frame took exactly
+// as long as the L2 needs to serialise them (1.25 ns per same-address atomic, 322 us) whatever the traversal cost -- the
+// counter, not the BVH walk, was the bound.  Without it the same frame takes 279 us and per-visit savings show up again.
+// Primary mode traces only the tiles that touch the caller's cull rectangle (blocks [0, trace_blocks), 2x2 tiles each);
+// the rest of the pixel rect is written as misses by the clear blocks that follow them in the grid.
+//
+// Measured on B200 and NOT adopted (4K frame, dragon100k; all under the counter-bound loop, so only the losses are
+// conclusive): claiming the next tile early (+6 %), claiming 8 tiles per atomic (+65 %: the tail grows), entry distances on
+// the stack for pop-time culling (+10 %), per-lane refill a la Aila-Laine, idle lanes claiming single pixels (+27 %: primary
+// rays are coherent, mixing tiles in a warp costs more in divergent node fetches than parked lanes do), a warp-synchronous
+// while-while loop that parks leaves and runs node steps and triangle tests in separate ballot-driven phases (+44 %: lanes
+// blocked on two parked leaves wait for the deepest lane of every phase).
+template <int MODE, bool STATS, bool FMA, bool VIEW>
 __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
 {
     int stack[STACK];
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const int tiles_x = MODE ? (a.w + 7) >> 3 : 1;
-    const long long n_units = MODE ? (long long)tiles_x * ((a.h + 3) >> 2) : (a.n_rays + 31) >> 5;
-    const float two_over_w = MODE ? 2.0f / (float)a.width : 0.0f, two_over_h = MODE ? 2.0f / (float)a.height : 0.0f;
-
-    // Measured on B200 and NOT adopted (4K frame, dragon100k, 322 us with this loop): claiming the next tile early (+6 %),
-    // claiming 8 tiles per atomic (+65 %: the tail grows), entry distances on the stack for pop-time culling (+10 %),
-    // per-lane refill a la Aila-Laine, idle lanes claiming single pixels (+27 %: primary rays are coherent, mixing tiles in
-    // a warp costs more in divergent node fetches than parked lanes do), a warp-synchronous while-while loop that parks leaves
-    // and runs node steps and triangle tests in separate ballot-driven phases (+44 %: lanes blocked on two parked leaves wait
-    // for the deepest lane of every phase), 12 instead of 10 resident blocks per SM via __launch_bounds__ (40 registers, +-0 %).
-    // The stall samples ncu books on this atomic are lanes waiting at the reconvergence point for the longest ray of their tile.
-    for (;;) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(a.ctl, 1u);
-        unit = __shfl_sync(FULL, unit, 0);
-        if ((long long)unit >= n_units) break;
-        if (MODE) {
-            const int tx = (int)(unit % (unsigned)tiles_x), ty = (int)(unit / (unsigned)tiles_x);
-            const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
-            if (lx >= a.w || ly >= a.h) continue;
-            const float sx = ((float)(a.x0 + lx) + 0.5f) * two_over_w - 1.0f;
-            const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * two_over_h;
-            const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
-            const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
-            const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
-            Hit h;
-            const int gx = a.x0 + lx, gy = a.y0 + ly;
-            if (gx < a.cull[0] || gy < a.cull[1] || gx > a.cull[2] || gy > a.cull[3]) {
-                h.t = INFINITY; h.u = 0.0f; h.v = 0.0f; h.id = 0xFFFFFFFFu; // outside the scene's screen bounds: a miss
-            } else {
-                h = trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (MODE) {
+        if ((int)blockIdx.x >= a.trace_blocks) { // clear block: four pixel rows of the rect, minus the traced tiles
+            const int band = (int)blockIdx.x - a.trace_blocks;
+            const bool traced_band = band >= a.tt[1] && band < a.tt[1] + a.tt[3];
+            const int skip0 = traced_band ? a.tt[0] * 8 : a.w, skip1 = traced_band ? (a.tt[0] + a.tt[2]) * 8 : a.w;
+            for (int r = 0; r < 4; ++r) {
+                const int ly = band * 4 + r;
+                if (ly >= a.h) break;
+                for (int lx = threadIdx.x; lx < a.w; lx += TB) {
+                    if (lx >= skip0 && lx < skip1) continue;
+                    if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(INFINITY, __uint_as_float(0xFFFFFFFFu), 0.0f, 0.0f);
+                    if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = 0u;
+                }
             }
-            const long long p = (long long)ly * a.w + lx;
-            if (a.hits) a.hits[p] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
-            if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
-        } else {
-            const long long r = (long long)unit * 32 + lane;
-            if (r >= a.n_rays) continue;
-            const float4 o = __ldg(a.rays + 2 * r), d = __ldg(a.rays + 2 * r + 1);
-            const Hit h = trace<STATS, false>(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
-            a.hits[r] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
+            return;
         }
-    }
-    // last block out re-arms the counters for the next launch
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(a.ctl + 1, 1u) == gridDim.x - 1) { a.ctl[0] = 0u; a.ctl[1] = 0u; }
+        const int bw = (a.tt[2] + 1) >> 1;
+        const int tx = a.tt[0] + 2 * ((int)blockIdx.x % bw) + (wid & 1), ty = a.tt[1] + 2 * ((int)blockIdx.x / bw) + (wid >> 1);
+        if (tx >= a.tt[0] + a.tt[2] || ty >= a.tt[1] + a.tt[3]) return;
+        const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
+        if (lx >= a.w || ly >= a.h) return;
+        const float sx = ((float)(a.x0 + lx) + 0.5f) * (2.0f / (float)a.width) - 1.0f;
+        const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * (2.0f / (float)a.height);
+        const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
+        const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
+        const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
+        const Hit h = VIEW ? trace_view<STATS>(a, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack)
+                           : trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+        if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
+        if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
+    } else {
+        const long long r = ((long long)blockIdx.x * (TB / 32) + wid) * 32 + lane;
+        if (r >= a.n_rays) return;
+        const float4 o = __ldg(a.rays + 2 * r), d = __ldg(a.rays + 2 * r + 1);
+        const Hit h = trace<STATS, false>(a, o.x, o.y, o.z, d.x, d.y, d.z, stack);
+        a.hits[r] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
     }
 }
 
-template <int MODE, bool STATS, bool FMA>
-int launch_trace_s(const TraceArgs &a, cudaStream_t st)
+template <int MODE, bool STATS, bool FMA, bool VIEW>
+int launch_trace_s(TraceArgs &a, cudaStream_t st)
 {
-    static int per_sm = 0; // per instantiation; the occupancy query costs ~10 us of host time
-    if (per_sm == 0) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<MODE, STATS, FMA>, TB, 0));
-    raycast_kernel<MODE, STATS, FMA><<<rt_sm_count() * (per_sm > 0 ? per_sm : 1), TB, 0, st>>>(a);
+    long long blocks;
+    if (MODE) {
+        // traced tile rectangle: the 8x4 tiles of the pixel rect that touch the cull rectangle (frame pixels, inclusive)
+        const int cx0 = (a.cull[0] > a.x0 ? a.cull[0] : a.x0) - a.x0, cy0 = (a.cull[1] > a.y0 ? a.cull[1] : a.y0) - a.y0;
+        const int cx1 = (a.cull[2] < a.x0 + a.w - 1 ? a.cull[2] : a.x0 + a.w - 1) - a.x0;
+        const int cy1 = (a.cull[3] < a.y0 + a.h - 1 ? a.cull[3] : a.y0 + a.h - 1) - a.y0;
+        if (cx1 < cx0 || cy1 < cy0) { a.tt[0] = a.tt[1] = a.tt[2] = a.tt[3] = 0; }
+        else { a.tt[0] = cx0 >> 3; a.tt[1] = cy0 >> 2; a.tt[2] = (cx1 >> 3) - a.tt[0] + 1; a.tt[3] = (cy1 >> 2) - a.tt[1] + 1; }
+        a.trace_blocks = ((a.tt[2] + 1) >> 1) * ((a.tt[3] + 1) >> 1);
+        const bool all_traced = a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
+        blocks = (long long)a.trace_blocks + (all_traced ? 0 : (a.h + 3) >> 2);
+    } else {
+        blocks = (a.n_rays + TB - 1) / TB;
+    }
+    if (blocks > 0) raycast_kernel<MODE, STATS, FMA, VIEW><<<(unsigned)blocks, TB, 0, st>>>(a);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
 
 template <int MODE>
-int launch_trace(const TraceArgs &a, bool fma, cudaStream_t st)
+int launch_trace(TraceArgs &a, bool fma, cudaStream_t st)
 {
-    if (a.stats) return fma ? launch_trace_s<MODE, true, true>(a, st) : launch_trace_s<MODE, true, false>(a, st);
-    return fma ? launch_trace_s<MODE, false, true>(a, st) : launch_trace_s<MODE, false, false>(a, st);
+    if constexpr (MODE != 0) {
+        if (a.vnodes) return a.stats ? launch_trace_s<MODE, true, false, true>(a, st) : launch_trace_s<MODE, false, false, true>(a, st);
+    }
+    if (a.stats) return fma ? launch_trace_s<MODE, true, true, false>(a, st) : launch_trace_s<MODE, true, false, false>(a, st);
+    return fma ? launch_trace_s<MODE, false, true, false>(a, st) : launch_trace_s<MODE, false, false, false>(a, st);
+}
+
+// [U V W]^-1 in double and the rectangle padding (see project_kernel); false if the camera basis is singular
+bool camera_inverse(const float *cam, ProjectArgs &p)
+{
+    const double U[3] = {cam[3], cam[4], cam[5]}, V[3] = {cam[6], cam[7], cam[8]}, W[3] = {cam[9], cam[10], cam[11]};
+    // M = [U V W] (columns); rows of the inverse are cross products over the determinant
+    const double c0[3] = {V[1] * W[2] - V[2] * W[1], V[2] * W[0] - V[0] * W[2], V[0] * W[1] - V[1] * W[0]};
+    const double c1[3] = {W[1] * U[2] - W[2] * U[1], W[2] * U[0] - W[0] * U[2], W[0] * U[1] - W[1] * U[0]};
+    const double c2[3] = {U[1] * V[2] - U[2] * V[1], U[2] * V[0] - U[0] * V[2], U[0] * V[1] - U[1] * V[0]};
+    const double det = U[0] * c0[0] + U[1] * c0[1] + U[2] * c0[2];
+    if (!(det != 0.0) || !(det - det == 0.0)) return false;
+    double rowsum = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        p.minv[k] = c0[k] / det; p.minv[3 + k] = c1[k] / det; p.minv[6 + k] = c2[k] / det;
+    }
+    for (int r = 0; r < 3; ++r) {
+        const double rs = fabs(p.minv[3 * r]) + fabs(p.minv[3 * r + 1]) + fabs(p.minv[3 * r + 2]);
+        rowsum = rs > rowsum ? rs : rowsum;
+        if (!(rs - rs == 0.0)) return false;
+    }
+    double dmax = 0.0; // bound of |direction component| over the frame, |sx|, |sy| <= 1
+    for (int k = 0; k < 3; ++k) {
+        const double d = fabs(U[k]) + fabs(V[k]) + fabs(W[k]);
+        dmax = d > dmax ? d : dmax;
+    }
+    const double pad = 8.0 * rowsum * dmax * 2.384185791015625e-7; // 8 x rowsum x 2^-22 dmax
+    if (!(pad < 1e-3)) return false; // ill-conditioned basis: not worth it, walk the 3-D nodes
+    p.pad_s = (float)pad;
+    p.o[0] = cam[0]; p.o[1] = cam[1]; p.o[2] = cam[2];
+    return true;
 }
 
 } // namespace
@@ -232,26 +428,26 @@ int launch_trace(const TraceArgs &a, bool fma, cudaStream_t st)
 extern "C" {
 
 int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_rays, int64_t n_rays, void *d_hits,
-                    void *d_ctl, void *stream)
+                    void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
     RT_REQUIRE(n_rays >= 0 && n_rays < (1ll << 36), "ray count");
     if (n_rays == 0) return RT_OK;
-    RT_REQUIRE(d_rays && d_hits && d_ctl, "ray / hit / control buffers");
+    RT_REQUIRE(d_rays && d_hits, "ray / hit buffers");
     RT_REQUIRE((((uintptr_t)d_rays | (uintptr_t)d_hits) & 15) == 0, "16-byte alignment");
     TraceArgs a = {};
     a.nodes = (const RtBvhNode *)d_nodes; a.tris = (const RtBvhTri *)d_tris;
-    a.rays = (const float4 *)d_rays; a.n_rays = n_rays; a.hits = (float4 *)d_hits; a.ctl = (unsigned *)d_ctl;
+    a.rays = (const float4 *)d_rays; a.n_rays = n_rays; a.hits = (float4 *)d_hits;
     return launch_trace<0>(a, false, (cudaStream_t)stream);
 }
 
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4, const void *d_nrm4,
                        const int32_t *d_indices, const float *camera, int width, int height, int x0, int y0, int w, int h, int shader,
-                       uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_ctl, void *d_stats,
-                       const int *cull_rect, int fast_slab, void *stream)
+                       uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_stats,
+                       const int *cull_rect, int fast_slab, void *d_view_nodes, void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
-    RT_REQUIRE(camera && d_ctl, "camera / control block");
+    RT_REQUIRE(camera, "camera");
     RT_REQUIRE(width > 0 && height > 0 && w >= 0 && h >= 0 && x0 >= 0 && y0 >= 0 && x0 + w <= width && y0 + h <= height, "pixel rect");
     RT_REQUIRE(shader == RT_SHADER_LESSON08 || shader == RT_SHADER_LESSON09, "shader id");
     RT_REQUIRE(!d_bgra || (d_nrm4 && bgra_pitch_px >= w), "shading needs normals and a pitch >= w");
@@ -262,10 +458,20 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     for (int i = 0; i < 12; ++i) a.cam[i] = camera[i];
     a.width = width; a.height = height; a.x0 = x0; a.y0 = y0; a.w = w; a.h = h;
     a.hits = (float4 *)d_hits; a.bgra = (uint32_t *)d_bgra; a.pitch_px = bgra_pitch_px;
-    a.pos = (const float4 *)d_pos4; a.nrm = (const float4 *)d_nrm4; a.idx = d_indices; a.ctl = (unsigned *)d_ctl;
+    a.pos = (const float4 *)d_pos4; a.nrm = (const float4 *)d_nrm4; a.idx = d_indices;
     a.stats = (unsigned long long *)d_stats;
     a.cull[0] = cull_rect ? cull_rect[0] : 0; a.cull[1] = cull_rect ? cull_rect[1] : 0;
     a.cull[2] = cull_rect ? cull_rect[2] : width - 1; a.cull[3] = cull_rect ? cull_rect[3] : height - 1;
+    if (d_view_nodes) {
+        RT_REQUIRE(((uintptr_t)d_view_nodes & 15) == 0, "view nodes must be 16-byte aligned");
+        ProjectArgs p = {};
+        if (camera_inverse(camera, p)) {
+            p.nodes = a.nodes; p.vnodes = (ViewNode *)d_view_nodes; p.n_inner = n_triangles > 1 ? n_triangles - 1 : 1;
+            project_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+            RT_CUDA(cudaGetLastError());
+            a.vnodes = p.vnodes;
+        }
+    }
     if (shader == RT_SHADER_LESSON09) {
         RT_REQUIRE(!d_bgra || (tex_handle != 0 && d_pos4), "lesson09 shading needs a texture handle and positions");
         if (tex_handle) {
@@ -275,6 +481,11 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
         return launch_trace<9>(a, fast_slab != 0, (cudaStream_t)stream);
     }
     return launch_trace<8>(a, fast_slab != 0, (cudaStream_t)stream);
+}
+
+int64_t rt_raycast_view_node_bytes(int64_t n_triangles)
+{
+    return (int64_t)sizeof(ViewNode) * (n_triangles > 1 ? n_triangles - 1 : 1);
 }
 
 } // extern "C"

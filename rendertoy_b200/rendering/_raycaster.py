@@ -22,6 +22,10 @@ from . import _core
 from ._core import kernel_struct, float3, create_buffer, stream_ptr, DeviceBuffer
 from ._modeling import Mesh
 
+# render(): above this size the per-frame projection of the BVH (reads 64 B, writes 48 B per node) costs more than
+# the cheaper node test saves
+VIEW_NODES_MAX_TRIANGLES = 1 << 18
+
 
 @kernel_struct
 class BVH_AABB:
@@ -125,10 +129,10 @@ class Raycaster:
         self.nodes = torch.empty(int(L.rt_bvh_node_bytes(n)), dtype=torch.uint8, device=dev)
         self.tris = torch.empty(int(L.rt_bvh_tri_bytes(n)), dtype=torch.uint8, device=dev)
         scratch = torch.empty(int(L.rt_bvh_scratch_bytes(n)), dtype=torch.uint8, device=dev)
-        self.ctl = torch.zeros(256, dtype=torch.uint8, device=dev)
         _native.call("rt_bvh_build", self.pos4.data_ptr(), self._idx_ptr(), n, self.nodes.data_ptr(), self.tris.data_ptr(),
                      scratch.data_ptr(), stream_ptr())
         self._build_scratch = scratch  # kept until the stream has consumed it
+        self._view_nodes = None        # per-frame screen-space nodes of render(), allocated on first use
 
     def _idx_ptr(self):
         return None if self.indices is None else self.indices.data_ptr()
@@ -140,7 +144,7 @@ class Raycaster:
         assert rays.dtype.itemsize == 32, "rays must be Ray {origin: float3, direction: float3} (32 bytes)"
         hits = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.pos4.device)
         _native.call("rt_raycast_rays", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, rays.ptr, n,
-                     hits.data_ptr(), self.ctl.data_ptr(), stream_ptr())
+                     hits.data_ptr(), stream_ptr())
         return hits[:n]
 
     def ray_cast(self, rays: DeviceBuffer) -> DeviceBuffer:
@@ -183,12 +187,14 @@ class Raycaster:
 
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
-               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True):
+               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True, view_nodes=None):
         """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
         shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
         hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
         hits are wanted (then frame_size=(W, H) is required).  stats: optional int64[3] tensor; the instrumented kernel
-        adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds."""
+        adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds.
+        view_nodes: project the BVH into this camera's screen space first and traverse that (default: yes up to
+        VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself)."""
         if render_target is not None:
             W, H = render_target.width, render_target.height
         else:
@@ -213,10 +219,18 @@ class Raycaster:
                 import ctypes
                 rect_c = (ctypes.c_int * 4)(*r)
         fast_slab = int(float(np.abs(cam32[0:3]).max()) <= 16.0 * self.scene_extent)
+        if view_nodes is None:
+            view_nodes = self.n_triangles <= VIEW_NODES_MAX_TRIANGLES
+        vn_ptr = None
+        if view_nodes:
+            if self._view_nodes is None:
+                self._view_nodes = torch.empty(int(_native.lib().rt_raycast_view_node_bytes(self.n_triangles)), dtype=torch.uint8,
+                                               device=self.pos4.device)
+            vn_ptr = self._view_nodes.data_ptr()
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
                      self.nrm4.data_ptr(), self._idx_ptr(),
                      _native.float_array_from_bytes(cam32.view(np.uint8), 12),
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
-                     self.ctl.data_ptr(), None if stats is None else stats.data_ptr(), rect_c, fast_slab, stream_ptr())
+                     None if stats is None else stats.data_ptr(), rect_c, fast_slab, vn_ptr, stream_ptr())
         if render_target is not None:
             render_target._buffer.device_written()

@@ -160,3 +160,52 @@ def test_full_size_matches_cpu_bvh_and_raster(ren, oracle):
     cover = ((ray_id != 0xFFFFFFFF) == (ras_id != 0xFFFFFFFF)).mean()
     print(f"raster-vs-raycast: same triangle on {same:.4f} of commonly covered pixels, coverage agreement {cover:.4f}")
     assert same > 0.97 and cover > 0.99
+
+
+def _hits(rc, cam, w, h, **kw):
+    hits = torch.empty((w * h, 4), dtype=torch.float32, device="cuda")
+    rc.render(None, cam, hits=hits, frame_size=(w, h), **kw)
+    return hits.cpu().numpy().view(np.uint32)
+
+
+def test_view_space_nodes_give_the_same_hits(ren, oracle):
+    """render() projects the BVH into the camera's screen space once per frame and walks that (rectangle tests);
+    the hit records must be bit-identical to the 3-D slab traversal for every camera -- also with the eye inside
+    the scene's bounds (nodes straddling the eye plane), grazing views and a stretched camera basis."""
+    from rendering._raycaster import Raycaster
+    rows = scenes.dragon(20_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    w, h = 640, 360
+    cams = [_camera(ren, 6, t, w, h) for t in (0.0, 0.7, 2.1)] + [_camera(ren, 8, 1.3, w, h)]
+    inside = np.array(cams[0], dtype=np.float32).copy()
+    inside[0:3] = (0.02, 0.01, 0.03)                        # eye in the middle of the mesh
+    cams.append(inside)
+    skew = np.array(cams[1], dtype=np.float32).copy()
+    skew[3:6] *= 7.0                                        # very wide, anisotropic basis
+    skew[6:9] *= 0.05
+    cams.append(skew)
+    for i, cam in enumerate(cams):
+        a = _hits(rc, cam, w, h, view_nodes=True)
+        b = _hits(rc, cam, w, h, view_nodes=False)
+        assert np.array_equal(a, b), f"camera {i}: {int((a != b).any(axis=1).sum())} pixels differ"
+    # brute force on a subset, so the two paths are not merely equal to each other
+    ref = oracle.raycast_brute(rows, oracle.primary_rays(inside, 64, 36))
+    _check(_hits(rc, inside, 64, 36, view_nodes=True).view(np.float32), ref, "eye inside the mesh, view nodes")
+
+
+def test_view_space_nodes_degenerate_scenes(ren, oracle):
+    from rendering._raycaster import Raycaster
+    w, h = 96, 64
+    cam = _camera(ren, 6, 0.4, w, h)
+    one = scenes.dragon(12)[:3].copy()                      # a single triangle: root with an empty second child
+    bad = scenes.dragon(300).copy()
+    bad[7, 0] = np.nan                                      # non-finite vertices poison some boxes
+    bad[40, 1] = np.inf
+    bad[91, 2] = -np.inf
+    for label, rows in (("single triangle", one), ("non-finite vertices", bad)):
+        rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+        a = _hits(rc, cam, w, h, view_nodes=True)
+        b = _hits(rc, cam, w, h, view_nodes=False)
+        assert np.array_equal(a, b), label
+        ref = oracle.raycast_brute(rows, oracle.primary_rays(cam, w, h))
+        _check(a.view(np.float32), ref, label)

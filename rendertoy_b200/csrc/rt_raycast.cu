@@ -11,11 +11,19 @@
 // Bound: FP32 pipe + L1/L2 latency (the BVH of a 100k-triangle mesh is ~11 MB, L2-resident); HBM sees only the
 // frame.  No contraction anywhere, so no tensor cores.
 #include "rt_common.cuh"
+#include <cstdlib>
 #include "rt_bvh.cuh"
 
 namespace {
 
-constexpr int TB = 128;   // threads per block
+#ifndef RT_RAYCAST_TB
+#define RT_RAYCAST_TB 128
+#endif
+#ifndef RT_RAYCAST_MINB
+#define RT_RAYCAST_MINB 12 // 40 registers: 48 of 64 warps resident (2 % over the unconstrained 46-register build)
+#endif
+constexpr int TB = RT_RAYCAST_TB;   // threads per block
+constexpr int TILES_BX = TB >= 64 ? 2 : 1, TILES_BY = TB / 32 / TILES_BX; // tiles of one block
 constexpr int STACK = 64; // Karras tree depth <= 64 (32 key bits + index tiebreak), one pending sibling per level
 // The per-lane stack lives in local memory (L1-resident, only the touched depth is ever cached).  Measured on B200
 // against a [depth][thread] shared-memory stack: 332 vs 374 us per 4K frame -- the 32 KB of shared memory per CTA
@@ -124,6 +132,7 @@ struct TraceArgs {
     int tex_w, tex_h;
     int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
     int tt[4];     // primary mode: traced tile rectangle {tile x0, tile y0, tiles wide, tiles high} (8x4-pixel tiles of the rect)
+    int packet;       // experiment: packet traversal of the view nodes
     int trace_blocks; // primary mode: blocks [0, trace_blocks) trace 2x2 tiles each, the rest clear
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
@@ -277,6 +286,84 @@ __device__ __forceinline__ Hit trace_view(const TraceArgs &a, float sx, float sy
     return h;
 }
 
+// Packet form of trace_view(): the 32 rays of a tile walk the hierarchy TOGETHER.  In screen space the traversal order
+// (nearer c_min first) does not depend on the ray, so one warp-wide stack visits exactly the union of the nodes the lanes
+// would visit on their own, each lane still culling with its own tbest through its vote.  Node and triangle fetches become
+// one broadcast load per warp instead of up to 32 divergent ones, control flow is warp-uniform, and the stack (node,
+// voters, c_min) lives in shared memory.  ALL lanes of the warp must call (lanes without a pixel pass live = false).
+template <bool STATS>
+__device__ __forceinline__ Hit trace_view_packet(const TraceArgs &a, bool live, float sx, float sy, float ox, float oy, float oz, float dx,
+                                                 float dy, float dz, int4 *wstack /* [STACK], per warp, shared memory */)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned long long best = ~0ull;
+    float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
+    unsigned n_nodes = 0, n_tests = 0;
+    int sp = 0, cur = 0;
+    unsigned voters = __ballot_sync(FULL, live);
+    while (voters != 0u) {
+        if (cur >= 0) {
+            if (STATS && ((voters >> lane) & 1u)) ++n_nodes;
+            const float4 *np = reinterpret_cast<const float4 *>(a.vnodes + cur);
+            const float4 r0 = __ldg(np), r1 = __ldg(np + 1), zc = __ldg(np + 2);
+            const bool h0 = live && sx >= r0.x && sx <= r0.y && sy >= r0.z && sy <= r0.w && zc.x <= tbest;
+            const bool h1 = live && sx >= r1.x && sx <= r1.y && sy >= r1.z && sy <= r1.w && zc.y <= tbest;
+            const unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+            const int c0 = __float_as_int(zc.z), c1 = __float_as_int(zc.w);
+            if (m0 != 0u && m1 != 0u) {
+                const bool swap = zc.y < zc.x;
+                if (lane == 0) wstack[sp] = make_int4(swap ? c0 : c1, (int)(swap ? m0 : m1), __float_as_int(swap ? zc.x : zc.y), 0);
+                __syncwarp();
+                ++sp;
+                cur = swap ? c1 : c0; voters = swap ? m1 : m0;
+                continue;
+            }
+            if (m0 != 0u) { cur = c0; voters = m0; continue; }
+            if (m1 != 0u) { cur = c1; voters = m1; continue; }
+        } else if ((voters >> lane) & 1u) {
+            if (STATS) ++n_tests;
+            const float4 *tp = reinterpret_cast<const float4 *>(a.tris + ~cur);
+            const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+            // Moller-Trumbore, operation for operation as oracle/raycast_oracle.c: rc_moller_trumbore
+            const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
+            const float det = (e1.x * px + e1.y * py) + e1.z * pz;
+            if (det != 0.0f) {
+                const float inv = 1.0f / det;
+                const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
+                const float u = ((tx * px + ty * py) + tz * pz) * inv;
+                if (u >= 0.0f && !(u > 1.0f)) {
+                    const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
+                    const float v = ((dx * qx + dy * qy) + dz * qz) * inv;
+                    if (v >= 0.0f && !(u + v > 1.0f)) {
+                        const float t = ((e2.x * qx + e2.y * qy) + e2.z * qz) * inv;
+                        if (t > 0.0f && t != INFINITY) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(v0.w);
+                            if (key < best) { best = key; tbest = t; bu = u; bv = v; }
+                        }
+                    }
+                }
+            }
+        }
+        // pop the nearest pending subtree some voter still needs (their tbest may have shrunk since the push)
+        voters = 0u;
+        while (sp > 0) {
+            --sp;
+            const int4 e = wstack[sp];
+            const unsigned m = __ballot_sync(FULL, (((unsigned)e.y >> lane) & 1u) && __int_as_float(e.z) <= tbest);
+            if (m != 0u) { cur = e.x; voters = m; break; }
+        }
+    }
+    if (STATS && live) {
+        atomicAdd(a.stats, (unsigned long long)n_nodes);
+        atomicAdd(a.stats + 1, (unsigned long long)n_tests);
+        atomicAdd(a.stats + 2, 1ull);
+    }
+    Hit h;
+    h.t = tbest; h.u = bu; h.v = bv; h.id = best == ~0ull ? 0xFFFFFFFFu : (unsigned)best;
+    return h;
+}
+
 // Lambert / texture shade of a hit, as oracle/raycast_oracle.c: orc_shade_hits
 template <int SHADER>
 __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
@@ -317,7 +404,7 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 // while-while loop that parks leaves and runs node steps and triangle tests in separate ballot-driven phases (+44 %: lanes
 // blocked on two parked leaves wait for the deepest lane of every phase).
 template <int MODE, bool STATS, bool FMA, bool VIEW>
-__global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
+__global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const TraceArgs a)
 {
     int stack[STACK];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -337,18 +424,26 @@ __global__ void __launch_bounds__(TB) raycast_kernel(const TraceArgs a)
             }
             return;
         }
-        const int bw = (a.tt[2] + 1) >> 1;
-        const int tx = a.tt[0] + 2 * ((int)blockIdx.x % bw) + (wid & 1), ty = a.tt[1] + 2 * ((int)blockIdx.x / bw) + (wid >> 1);
+        const int bw = (a.tt[2] + TILES_BX - 1) / TILES_BX;
+        const int tx = a.tt[0] + TILES_BX * ((int)blockIdx.x % bw) + wid % TILES_BX, ty = a.tt[1] + TILES_BY * ((int)blockIdx.x / bw) + wid / TILES_BX;
         if (tx >= a.tt[0] + a.tt[2] || ty >= a.tt[1] + a.tt[3]) return;
         const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
-        if (lx >= a.w || ly >= a.h) return;
+        const bool live = lx < a.w && ly < a.h;
+        if (!VIEW && !live) return;
         const float sx = ((float)(a.x0 + lx) + 0.5f) * (2.0f / (float)a.width) - 1.0f;
         const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * (2.0f / (float)a.height);
         const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
         const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
         const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
-        const Hit h = VIEW ? trace_view<STATS>(a, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack)
-                           : trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+        Hit h;
+        if (VIEW) {
+            __shared__ int4 wstacks[TB / 32][STACK];
+            if (a.packet) h = trace_view_packet<STATS>(a, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstacks[wid]);
+            else if (live) h = trace_view<STATS>(a, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+            if (!live) return;
+        } else {
+            h = trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+        }
         if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
         if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
     } else {
@@ -371,12 +466,14 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
         const int cy1 = (a.cull[3] < a.y0 + a.h - 1 ? a.cull[3] : a.y0 + a.h - 1) - a.y0;
         if (cx1 < cx0 || cy1 < cy0) { a.tt[0] = a.tt[1] = a.tt[2] = a.tt[3] = 0; }
         else { a.tt[0] = cx0 >> 3; a.tt[1] = cy0 >> 2; a.tt[2] = (cx1 >> 3) - a.tt[0] + 1; a.tt[3] = (cy1 >> 2) - a.tt[1] + 1; }
-        a.trace_blocks = ((a.tt[2] + 1) >> 1) * ((a.tt[3] + 1) >> 1);
+        a.trace_blocks = ((a.tt[2] + TILES_BX - 1) / TILES_BX) * ((a.tt[3] + TILES_BY - 1) / TILES_BY);
         const bool all_traced = a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
         blocks = (long long)a.trace_blocks + (all_traced ? 0 : (a.h + 3) >> 2);
     } else {
         blocks = (a.n_rays + TB - 1) / TB;
     }
+    static const bool packet = getenv("RT_RAYCAST_NO_PACKET") == nullptr;
+    a.packet = packet;
     if (blocks > 0) raycast_kernel<MODE, STATS, FMA, VIEW><<<(unsigned)blocks, TB, 0, st>>>(a);
     RT_CUDA(cudaGetLastError());
     return RT_OK;

@@ -34,7 +34,7 @@ def run(n_tris, w, h, lesson, frames=20):
 
 if __name__ == "__main__":
     fr = 3 if len(sys.argv) > 1 and sys.argv[1] == "ncu" else 20
-    run(100_000, 3840, 2160, 6, fr)
+    run(100_000, 3840, 2160, 6, fr); sys.stdout.flush()
     run(100_000, 3840, 2160, 8, fr)
     if fr > 3:
         run(100_000, 1920, 1080, 8, fr)

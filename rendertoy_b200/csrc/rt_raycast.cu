@@ -11,7 +11,6 @@
 // Bound: FP32 pipe + L1/L2 latency (the BVH of a 100k-triangle mesh is ~11 MB, L2-resident); HBM sees only the
 // frame.  No contraction anywhere, so no tensor cores.
 #include "rt_common.cuh"
-#include <cstdlib>
 #include "rt_bvh.cuh"
 
 namespace {
@@ -132,7 +131,6 @@ struct TraceArgs {
     int tex_w, tex_h;
     int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
     int tt[4];     // primary mode: traced tile rectangle {tile x0, tile y0, tiles wide, tiles high} (8x4-pixel tiles of the rect)
-    int packet;       // experiment: packet traversal of the view nodes
     int trace_blocks; // primary mode: blocks [0, trace_blocks) trace 2x2 tiles each, the rest clear
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
@@ -222,71 +220,7 @@ __device__ __forceinline__ Hit trace(const TraceArgs &a, float ox, float oy, flo
     return h;
 }
 
-// trace() over this frame's ViewNodes: same stack discipline, same exact triangle test, box tests in screen space.
-template <bool STATS>
-__device__ __forceinline__ Hit trace_view(const TraceArgs &a, float sx, float sy, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          int *stack)
-{
-    unsigned long long best = ~0ull;
-    float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
-    int sp = 0, cur = 0;
-    unsigned n_nodes = 0, n_tests = 0;
-    for (;;) {
-        if (cur >= 0) {
-            if (STATS) ++n_nodes;
-            const float4 *np = reinterpret_cast<const float4 *>(a.vnodes + cur);
-            const float4 r0 = __ldg(np), r1 = __ldg(np + 1), zc = __ldg(np + 2);
-            const bool h0 = sx >= r0.x && sx <= r0.y && sy >= r0.z && sy <= r0.w && zc.x <= tbest;
-            const bool h1 = sx >= r1.x && sx <= r1.y && sy >= r1.z && sy <= r1.w && zc.y <= tbest;
-            const int c0 = __float_as_int(zc.z), c1 = __float_as_int(zc.w);
-            if (h0 && h1) {
-                const bool swap = zc.y < zc.x;
-                stack[sp] = swap ? c0 : c1;
-                ++sp;
-                cur = swap ? c1 : c0;
-                continue;
-            }
-            if (h0) { cur = c0; continue; }
-            if (h1) { cur = c1; continue; }
-        } else {
-            if (STATS) ++n_tests;
-            const float4 *tp = reinterpret_cast<const float4 *>(a.tris + ~cur);
-            const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-            // Moller-Trumbore, operation for operation as oracle/raycast_oracle.c: rc_moller_trumbore
-            const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
-            const float det = (e1.x * px + e1.y * py) + e1.z * pz;
-            if (det != 0.0f) {
-                const float inv = 1.0f / det;
-                const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
-                const float u = ((tx * px + ty * py) + tz * pz) * inv;
-                if (u >= 0.0f && !(u > 1.0f)) {
-                    const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
-                    const float v = ((dx * qx + dy * qy) + dz * qz) * inv;
-                    if (v >= 0.0f && !(u + v > 1.0f)) {
-                        const float t = ((e2.x * qx + e2.y * qy) + e2.z * qz) * inv;
-                        if (t > 0.0f && t != INFINITY) {
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(v0.w);
-                            if (key < best) { best = key; tbest = t; bu = u; bv = v; }
-                        }
-                    }
-                }
-            }
-        }
-        if (sp == 0) break;
-        --sp;
-        cur = stack[sp];
-    }
-    if (STATS) {
-        atomicAdd(a.stats, (unsigned long long)n_nodes);
-        atomicAdd(a.stats + 1, (unsigned long long)n_tests);
-        atomicAdd(a.stats + 2, 1ull);
-    }
-    Hit h;
-    h.t = tbest; h.u = bu; h.v = bv; h.id = best == ~0ull ? 0xFFFFFFFFu : (unsigned)best;
-    return h;
-}
-
-// Packet form of trace_view(): the 32 rays of a tile walk the hierarchy TOGETHER.  In screen space the traversal order
+// Traversal of this frame's ViewNodes: the 32 rays of a tile walk the hierarchy TOGETHER.  In screen space the traversal order
 // (nearer c_min first) does not depend on the ray, so one warp-wide stack visits exactly the union of the nodes the lanes
 // would visit on their own, each lane still culling with its own tbest through its vote.  Node and triangle fetches become
 // one broadcast load per warp instead of up to 32 divergent ones, control flow is warp-uniform, and the stack (node,
@@ -387,6 +321,22 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
     return rt_pack_bgra(tx.x * d, tx.y * d, tx.z * d, 1.0f);
 }
 
+// Clear block: four pixel rows of the rect, minus the traced tiles, written as misses.
+__device__ __forceinline__ void clear_band(const TraceArgs &a, int band)
+{
+    const bool traced_band = band >= a.tt[1] && band < a.tt[1] + a.tt[3];
+    const int skip0 = traced_band ? a.tt[0] * 8 : a.w, skip1 = traced_band ? (a.tt[0] + a.tt[2]) * 8 : a.w;
+    for (int r = 0; r < 4; ++r) {
+        const int ly = band * 4 + r;
+        if (ly >= a.h) break;
+        for (int lx = threadIdx.x; lx < a.w; lx += TB) {
+            if (lx >= skip0 && lx < skip1) continue;
+            if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(INFINITY, __uint_as_float(0xFFFFFFFFu), 0.0f, 0.0f);
+            if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = 0u;
+        }
+    }
+}
+
 // MODE 0: rays from a buffer, hits out.  MODE 8 / 9: primary rays + shade with that lesson's shader.
 //
 // One warp per work unit (an 8x4-pixel tile or 32 consecutive rays), four units per block, and the hardware block
@@ -403,33 +353,25 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 // rays are coherent, mixing tiles in a warp costs more in divergent node fetches than parked lanes do), a warp-synchronous
 // while-while loop that parks leaves and runs node steps and triangle tests in separate ballot-driven phases (+44 %: lanes
 // blocked on two parked leaves wait for the deepest lane of every phase).
+// Measured after the counter was gone and NOT adopted (200 us with tile packets): per-lane stacks over the screen-space
+// nodes (241 us: divergent node fetches, 17 of 32 lanes active); 16x8 .. 32x16-pixel region packets, a cell of 2x2 .. 4x4
+// pixels per lane, hits in shared memory and the lanes re-dealt over each leaf's pixels (4x fewer node visits per ray, but
+// 290 - 485 us: with ~6-pixel triangles the per-leaf work dominates and gets more expensive); prefetching both children of
+// a node while the warp votes (+15 %: the loop is issue-bound, not latency-bound); 64- or 32-thread blocks (+5 - 10 %);
+// the packet walk over the 3-D nodes with per-lane slab tests (100k triangles: 228 vs 253 us per-lane, but 1M: 512 vs 407 us,
+// sub-pixel triangles leave nothing for a tile to share -- and below ~256k triangles the screen-space packets win anyway).
 template <int MODE, bool STATS, bool FMA, bool VIEW>
 __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const TraceArgs a)
 {
     int stack[STACK];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (MODE) {
-        if ((int)blockIdx.x >= a.trace_blocks) { // clear block: four pixel rows of the rect, minus the traced tiles
-            const int band = (int)blockIdx.x - a.trace_blocks;
-            const bool traced_band = band >= a.tt[1] && band < a.tt[1] + a.tt[3];
-            const int skip0 = traced_band ? a.tt[0] * 8 : a.w, skip1 = traced_band ? (a.tt[0] + a.tt[2]) * 8 : a.w;
-            for (int r = 0; r < 4; ++r) {
-                const int ly = band * 4 + r;
-                if (ly >= a.h) break;
-                for (int lx = threadIdx.x; lx < a.w; lx += TB) {
-                    if (lx >= skip0 && lx < skip1) continue;
-                    if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(INFINITY, __uint_as_float(0xFFFFFFFFu), 0.0f, 0.0f);
-                    if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = 0u;
-                }
-            }
-            return;
-        }
+        if ((int)blockIdx.x >= a.trace_blocks) { clear_band(a, (int)blockIdx.x - a.trace_blocks); return; }
         const int bw = (a.tt[2] + TILES_BX - 1) / TILES_BX;
         const int tx = a.tt[0] + TILES_BX * ((int)blockIdx.x % bw) + wid % TILES_BX, ty = a.tt[1] + TILES_BY * ((int)blockIdx.x / bw) + wid / TILES_BX;
         if (tx >= a.tt[0] + a.tt[2] || ty >= a.tt[1] + a.tt[3]) return;
         const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
         const bool live = lx < a.w && ly < a.h;
-        if (!VIEW && !live) return;
         const float sx = ((float)(a.x0 + lx) + 0.5f) * (2.0f / (float)a.width) - 1.0f;
         const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * (2.0f / (float)a.height);
         const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
@@ -438,10 +380,10 @@ __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const Trac
         Hit h;
         if (VIEW) {
             __shared__ int4 wstacks[TB / 32][STACK];
-            if (a.packet) h = trace_view_packet<STATS>(a, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstacks[wid]);
-            else if (live) h = trace_view<STATS>(a, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
+            h = trace_view_packet<STATS>(a, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstacks[wid]);
             if (!live) return;
         } else {
+            if (!live) return;
             h = trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
         }
         if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
@@ -472,8 +414,6 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
     } else {
         blocks = (a.n_rays + TB - 1) / TB;
     }
-    static const bool packet = getenv("RT_RAYCAST_NO_PACKET") == nullptr;
-    a.packet = packet;
     if (blocks > 0) raycast_kernel<MODE, STATS, FMA, VIEW><<<(unsigned)blocks, TB, 0, st>>>(a);
     RT_CUDA(cudaGetLastError());
     return RT_OK;

@@ -251,7 +251,7 @@ def bench_raycast(args, rank, world):
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     sm_count = torch.cuda.get_device_properties(0).multi_processor_count
     fp32_peak = sm_count * 128 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
-    flops = nodes * 2 * 22 + tests * 45          # totals of one full instrumented frame (culled pixels trace nothing)
+    flops = nodes * 10 + tests * 45              # totals of one full instrumented frame (culled pixels trace nothing)
     out = {
         "metric": METRIC_RAY, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -267,19 +267,21 @@ def bench_raycast(args, rank, world):
                    "bvh_build_excluded": True},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": ncu_traffic().get("raycast_kernel"), "peak_source": peak_src,
-                     "kernel": "raycast_kernel<8>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "HBM does not bind this kernel (BVH is L2-resident); the binding units are the FP32 pipe and "
-                             "L1/L2 latency, see fp32 and profiles/",
+                     "kernel": "raycast_kernel<8> (+ project_kernel, same launch pair)", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "HBM does not bind this kernel (BVH and its per-frame screen-space copy are L2-resident); the binding "
+                             "unit is the instruction issue rate (compares, votes, branches of the packet walk: ~67 % of issue "
+                             "slots busy in profiles/), see fp32 for the arithmetic it amounts to",
                      "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
                               "inner_node_visits_per_ray": nodes / (RAY_W * RAY_H), "triangle_tests_per_ray": tests / (RAY_W * RAY_H),
                               "rays_traced_fraction": rays / (RAY_W * RAY_H),
-                              "flop_model": "44 flop per inner node (2 slab tests) + 45 flop per Moller-Trumbore test; peak counts "
-                                            "FMA as 2 flop, this kernel is compiled -fmad=false for bit-exact parity"}},
+                              "flop_model": "per voting lane: 10 float compares per inner node (two screen rectangles + depth bound "
+                                            "each) + 45 flop per Moller-Trumbore test; peak counts FMA as 2 flop, this kernel is "
+                                            "compiled -fmad=false for bit-exact parity"}},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": 4 * RAY_W * RAY_H * F,
                 "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async D2H of the "
                                         "33 MB BGRA8 frame into pinned memory (PCIe-bound); every rank reads back its own frames"},
-        "gpu_launches": F * args.steps, "clocks": clocks,
+        "gpu_launches": 2 * F * args.steps, "clocks": clocks,   # project_kernel + raycast_kernel per frame
     }
     return out, rows
 

@@ -132,7 +132,7 @@ class Raycaster:
         _native.call("rt_bvh_build", self.pos4.data_ptr(), self._idx_ptr(), n, self.nodes.data_ptr(), self.tris.data_ptr(),
                      scratch.data_ptr(), stream_ptr())
         self._build_scratch = scratch  # kept until the stream has consumed it
-        self._view_nodes = None        # per-frame screen-space nodes of render(), allocated on first use
+        self._view_nodes = {}          # stream -> per-frame screen-space nodes of render() (scratch, allocated on first use)
 
     def _idx_ptr(self):
         return None if self.indices is None else self.indices.data_ptr()
@@ -223,10 +223,11 @@ class Raycaster:
             view_nodes = self.n_triangles <= VIEW_NODES_MAX_TRIANGLES
         vn_ptr = None
         if view_nodes:
-            if self._view_nodes is None:
-                self._view_nodes = torch.empty(int(_native.lib().rt_raycast_view_node_bytes(self.n_triangles)), dtype=torch.uint8,
-                                               device=self.pos4.device)
-            vn_ptr = self._view_nodes.data_ptr()
+            stream = stream_ptr()   # the scratch is rewritten by every call: one per stream, so frames on different streams may overlap
+            if stream not in self._view_nodes:
+                self._view_nodes[stream] = torch.empty(int(_native.lib().rt_raycast_view_node_bytes(self.n_triangles)), dtype=torch.uint8,
+                                                       device=self.pos4.device)
+            vn_ptr = self._view_nodes[stream].data_ptr()
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
                      self.nrm4.data_ptr(), self._idx_ptr(),
                      _native.float_array_from_bytes(cam32.view(np.uint8), 12),

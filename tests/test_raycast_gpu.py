@@ -209,3 +209,43 @@ def test_view_space_nodes_degenerate_scenes(ren, oracle):
         assert np.array_equal(a, b), label
         ref = oracle.raycast_brute(rows, oracle.primary_rays(cam, w, h))
         _check(a.view(np.float32), ref, label)
+
+
+def test_view_space_nodes_random_cameras(ren, oracle):
+    """Fuzz: 60 random camera frames (eye anywhere from inside the mesh to 40 extents away, arbitrary orientation and
+    roll, field of view from 2 to 170 degrees, anisotropic and sheared bases, odd frame sizes and sub-rectangles):
+    the screen-space packet traversal and the 3-D slab traversal must return bit-identical hit records."""
+    from rendering._raycaster import Raycaster
+    rng = np.random.default_rng(20240607)
+    rows = scenes.dragon(6_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    checked = hit_pixels = 0
+    for i in range(60):
+        w, h = int(rng.integers(17, 200)), int(rng.integers(9, 120))
+        eye = rng.normal(size=3)
+        eye *= (rng.choice([0.02, 0.3, 0.8, 2.0, 12.0, 40.0]) / np.linalg.norm(eye))
+        look = rng.normal(size=3) * 0.2 - eye if rng.random() < 0.8 else rng.normal(size=3)
+        fwd = look / np.linalg.norm(look)
+        up = rng.normal(size=3)
+        right = np.cross(up, fwd); right /= np.linalg.norm(right)
+        up = np.cross(fwd, right)
+        tan_half = np.tan(np.radians(rng.choice([2.0, 20.0, 45.0, 90.0, 170.0])) / 2)
+        U, V, W = right * tan_half * (w / h), up * tan_half, fwd.copy()
+        if rng.random() < 0.3:      # shear / anisotropy: still a basis, no longer orthogonal
+            U = U + 0.3 * V; W = W + 0.1 * U; V = V * rng.uniform(0.2, 3.0)
+        cam = np.concatenate([eye, U, V, W]).astype(np.float32)
+        rect = None
+        if rng.random() < 0.4:
+            x0, y0 = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 4))
+            rect = (x0, y0, int(rng.integers(1, w - x0 + 1)), int(rng.integers(1, h - y0 + 1)))
+        rw, rh = (rect[2], rect[3]) if rect else (w, h)
+        out = []
+        for vn in (True, False):
+            hits = torch.empty((rw * rh, 4), dtype=torch.float32, device="cuda")
+            rc.render(None, cam, rect=rect, hits=hits, frame_size=(w, h), view_nodes=vn, cull=bool(i % 2))
+            out.append(hits.cpu().numpy().view(np.uint32))
+        assert np.array_equal(out[0], out[1]), f"camera {i}: {int((out[0] != out[1]).any(axis=1).sum())} of {rw * rh} pixels differ"
+        checked += rw * rh
+        hit_pixels += int((out[0][:, 1] != 0xFFFFFFFF).sum())
+    print(f"{checked} pixels over 60 cameras, {hit_pixels} hits")
+    assert hit_pixels > 0.02 * checked, "the fuzz cameras should see the mesh often enough to mean something"

@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENDERTOY_B200_LIB") or os.path.join(HERE, "librendertoy_b200.so")   # override: A/B builds
 
+BVH_LBVH, BVH_PLOC = 0, 1
 SHADER_LESSON08 = 8
 SHADER_LESSON09 = 9
 NO_PRIMITIVE = 0xFFFFFFFF
@@ -30,7 +31,7 @@ SIGNATURES = {
     "rt_bvh_node_bytes": (_I64, [_I64]),
     "rt_bvh_tri_bytes": (_I64, [_I64]),
     "rt_bvh_scratch_bytes": (_I64, [_I64]),
-    "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _I32, _VP]),
     "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP]),
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
                                      _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),

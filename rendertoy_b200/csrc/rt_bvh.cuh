@@ -10,3 +10,11 @@ struct __align__(16) RtBvhNode { float4 n0, n1, n2; int4 n3; };
 // Leaf triangle in sorted order, 48 B: v0.w carries the ORIGINAL triangle id (bits); edges precomputed
 // (the same float subtraction Moller-Trumbore starts with, so results stay bit-identical to the oracle).
 struct __align__(16) RtBvhTri { float4 v0, e1, e2; };
+
+// rt_bvh_build's `builder` (include/rendertoy_b200.h) and the bound both builders keep: the traversal stacks hold
+// one pending sibling per level, 64 entries (Karras: 32 key bits + index tie-break; PLOC: checked after the build).
+#ifndef RT_BVH_LBVH
+#define RT_BVH_LBVH 0
+#define RT_BVH_PLOC 1
+#endif
+#define RT_BVH_MAX_HEIGHT 64

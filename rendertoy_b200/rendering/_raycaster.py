@@ -25,6 +25,8 @@ from ._modeling import Mesh
 # render(): above this size the per-frame projection of the BVH (reads 64 B, writes 48 B per node) costs more than
 # the cheaper node test saves
 VIEW_NODES_MAX_TRIANGLES = 1 << 18
+# default builder: clustering pays where the traversal is the bound (the screen-space packet path)
+PLOC_MAX_TRIANGLES = 1 << 18
 
 
 @kernel_struct
@@ -80,8 +82,11 @@ def camera_frame(view, proj, world=None):
 
 
 class Raycaster:
-    def __init__(self, models: typing.List[Mesh]):
+    def __init__(self, models: typing.List[Mesh], builder: str = None):
+        """builder: "ploc" (default up to PLOC_MAX_TRIANGLES: parallel locally-ordered clustering, the better tree) or
+        "lbvh" (Karras hierarchy, the faster build).  Both give the same hits; the reference takes only `models`."""
         self.models = models
+        self.builder = builder
         self._build_ads()
 
     def _build_ads(self):
@@ -129,8 +134,11 @@ class Raycaster:
         self.nodes = torch.empty(int(L.rt_bvh_node_bytes(n)), dtype=torch.uint8, device=dev)
         self.tris = torch.empty(int(L.rt_bvh_tri_bytes(n)), dtype=torch.uint8, device=dev)
         scratch = torch.empty(int(L.rt_bvh_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+        if self.builder is None:
+            self.builder = "ploc" if n <= PLOC_MAX_TRIANGLES else "lbvh"
+        assert self.builder in ("ploc", "lbvh"), "builder must be 'ploc' or 'lbvh'"
         _native.call("rt_bvh_build", self.pos4.data_ptr(), self._idx_ptr(), n, self.nodes.data_ptr(), self.tris.data_ptr(),
-                     scratch.data_ptr(), stream_ptr())
+                     scratch.data_ptr(), _native.BVH_PLOC if self.builder == "ploc" else _native.BVH_LBVH, stream_ptr())
         self._build_scratch = scratch  # kept until the stream has consumed it
         self._view_nodes = {}          # stream -> per-frame screen-space nodes of render() (scratch, allocated on first use)
 

@@ -249,3 +249,85 @@ def test_view_space_nodes_random_cameras(ren, oracle):
         hit_pixels += int((out[0][:, 1] != 0xFFFFFFFF).sum())
     print(f"{checked} pixels over 60 cameras, {hit_pixels} hits")
     assert hit_pixels > 0.02 * checked, "the fuzz cameras should see the mesh often enough to mean something"
+
+
+def _validate_tree(rc, label):
+    """Download the node array and check it is a proper binary tree over all leaves, rooted at 0, with child boxes that
+    contain everything below them.  Returns the height.  (Done before any traversal: a malformed tree could hang one.)"""
+    n = rc.n_triangles
+    nodes = rc.nodes.cpu().numpy().view(np.float32).reshape(-1, 16)[:max(n - 1, 1)]
+    tris = rc.tris.cpu().numpy().view(np.float32).reshape(-1, 12)[:n]
+    child = nodes.view(np.int32)[:, 12:14]
+    assert ((child >= -n) & (child < max(n - 1, 1))).all(), f"{label}: child reference out of range"
+    # leaf boxes straight from the triangles (unpadded): every ancestor box must contain them
+    v0, v1, v2 = tris[:, 0:3], tris[:, 0:3] + tris[:, 4:7], tris[:, 0:3] + tris[:, 8:11]
+    seen_leaf = np.zeros(n, dtype=np.int32)
+    seen_node = np.zeros(max(n - 1, 1), dtype=np.int32)
+    height = 0
+    stack = [(0, 1, None)]   # node, depth, box it must fit in: (lo, hi)
+    while stack:
+        node, depth, bound = stack.pop()
+        seen_node[node] += 1
+        assert seen_node[node] == 1, f"{label}: node {node} reached twice"
+        height = max(height, depth)
+        r = nodes[node]
+        boxes = [(np.array([r[0], r[2], r[8]]), np.array([r[1], r[3], r[9]])), (np.array([r[4], r[6], r[10]]), np.array([r[5], r[7], r[11]]))]
+        for k in range(2):
+            lo, hi = boxes[k]
+            c = int(child[node, k])
+            if n == 1 and k == 1:
+                continue                      # the single-triangle root's empty second child
+            if bound is not None and np.isfinite(lo).all() and np.isfinite(hi).all():
+                assert (lo >= bound[0]).all() and (hi <= bound[1]).all(), f"{label}: child box of node {node} sticks out of its parent's"
+            if c < 0:
+                s = ~c
+                seen_leaf[s] += 1
+                pts = np.stack([v0[s], v1[s], v2[s]])
+                if np.isfinite(pts).all():
+                    assert (pts.min(0) >= lo).all() and (pts.max(0) <= hi).all(), f"{label}: leaf {s} outside its box"
+            else:
+                stack.append((c, depth + 1, (lo, hi)))
+    assert (seen_leaf == 1).all(), f"{label}: {int((seen_leaf != 1).sum())} leaves not reached exactly once"
+    if n > 1:
+        assert (seen_node == 1).all(), f"{label}: unreachable inner nodes"
+    return height
+
+
+def test_ploc_builder_trees_and_hits(ren, oracle):
+    """rt_bvh_build(RT_BVH_PLOC): structurally valid trees (checked on the host before anything traverses them) for regular,
+    tiny, duplicate-heavy, skewed and non-finite inputs; the same hit records as the Karras tree and as brute force."""
+    from rendering._raycaster import Raycaster
+    rng = np.random.default_rng(5)
+    base = scenes.dragon(3_000)
+    scenes_ = {"dragon3k": base}
+    for k in (1, 2, 3, 4, 5, 33):
+        scenes_[f"first {k} triangles"] = base[:3 * k].copy()
+    dup = np.tile(base[:3], (700, 1))                           # 700 copies of one triangle: all Morton codes equal
+    scenes_["700 identical triangles"] = dup
+    chain = base[:3 * 400].copy()                                # geometrically growing triangles along a line: nearest
+    for t in range(400):                                         # neighbour is always the smaller one -- worst case for mutual pairs
+        chain[3 * t:3 * t + 3, 0:3] = base[0:3, 0:3] * (1.03 ** t) + np.array([1.03 ** t, 0, 0])
+    scenes_["growing chain"] = chain
+    bad = base.copy()
+    bad[rng.integers(0, bad.shape[0], 12), rng.integers(0, 3, 12)] = np.nan
+    bad[rng.integers(0, bad.shape[0], 6), rng.integers(0, 3, 6)] = np.inf
+    scenes_["non-finite vertices"] = bad
+    w, h = 128, 72
+    for label, rows in scenes_.items():
+        vb = _mesh_buffer(ren, np.ascontiguousarray(rows))
+        rc_p = Raycaster([ren.Mesh(vb, None)], builder="ploc")
+        rc_l = Raycaster([ren.Mesh(vb, None)], builder="lbvh")
+        hp, hl = _validate_tree(rc_p, label + " (ploc)"), _validate_tree(rc_l, label + " (lbvh)")
+        assert hp <= 64 and hl <= 64, f"{label}: tree heights {hp} / {hl} exceed the traversal stack"
+        finite = rows[np.isfinite(rows[:, :3]).all(axis=1), :3]
+        centre, ext = (finite.min(0) + finite.max(0)) / 2, float((finite.max(0) - finite.min(0)).max())
+        eye = centre + np.array([0.3, 0.4, -2.0]) * max(ext, 1e-3)
+        fwd = (centre - eye) / np.linalg.norm(centre - eye)
+        right = np.cross([0, 1, 0], fwd); right /= np.linalg.norm(right)
+        up = np.cross(fwd, right)
+        cam = np.concatenate([eye, right * 0.5 * w / h, up * 0.5, fwd]).astype(np.float32)
+        a, b = _hits(rc_p, cam, w, h), _hits(rc_l, cam, w, h)
+        assert np.array_equal(a, b), f"{label}: PLOC and LBVH trees give different hits on {int((a != b).any(axis=1).sum())} pixels"
+        ref = oracle.raycast_brute(np.ascontiguousarray(rows), oracle.primary_rays(cam, w, h))
+        _check(a.view(np.float32), ref, label)
+        print(f"{label}: n={rows.shape[0] // 3} heights ploc {hp} lbvh {hl}, hit pixels {int((a[:, 1] != 0xFFFFFFFF).sum())}")

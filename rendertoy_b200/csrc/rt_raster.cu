@@ -354,19 +354,21 @@ __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ri
                 }
             }
         }
-        // push the spans, at most 4 cells per lane per pass, and drain full warps of candidates
+        // push the spans, at most 4 cells per lane per pass, and drain full warps of candidates.  The stack is an
+        // unordered pool, so the pass's cells go in "column-major": all first cells, then all second cells, ... -- one
+        // ballot + popc per column instead of a prefix scan and a divergent store loop.
         int remaining = hi >= lo ? hi - lo + 1 : 0;
+        const unsigned lt_mask = (1u << lane) - 1u;
         while (__any_sync(FULL, remaining > 0)) {
             const int n = min(remaining, 4);
-            int pin = n;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int v = __shfl_up_sync(FULL, pin, d);
-                if (lane >= d) pin += v;
-            }
-            const int ptot = __shfl_sync(FULL, pin, 31);
             const unsigned head = ((unsigned)slot << 24) | ((unsigned)lrow << 12);
-            for (int j = 0; j < n; ++j) my_ring[pending + pin - n + j] = head | (unsigned)(lo + j);
+            int ptot = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned bj = __ballot_sync(FULL, n > j);
+                if (n > j) my_ring[pending + ptot + __popc(bj & lt_mask)] = head | (unsigned)(lo + j);
+                ptot += __popc(bj);
+            }
             lo += n; remaining -= n; pending += ptot;
             __syncwarp();
             while (pending >= 32) {

@@ -336,18 +336,21 @@ __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ri
                     const float ak = ea[k], tk = eb[k] * py, ck = ec[k];
                     // accepted(col) <=> !(sg * ((ak * px + tk) + ck) < 0), px = x0 + col  (same expression as cell_eval)
                     const float dir = sg * ak;
-                    if (dir > 0.0f) {        // accepted for col >= L
-                        int L = __float2int_ru(__fdividef(-(tk + ck), ak) - x0);
-                        L = min(max(L, lo), hi + 1);
-                        while (L > lo && !(sg * ((ak * (x0 + (float)(L - 1)) + tk) + ck) < 0.0f)) --L;
-                        while (L <= hi && (sg * ((ak * (x0 + (float)L) + tk) + ck) < 0.0f)) ++L;
-                        lo = L;
-                    } else if (dir < 0.0f) { // accepted for col <= U
-                        int U = __float2int_rd(__fdividef(-(tk + ck), ak) - x0);
-                        U = min(max(U, lo - 1), hi);
-                        while (U < hi && !(sg * ((ak * (x0 + (float)(U + 1)) + tk) + ck) < 0.0f)) ++U;
-                        while (U >= lo && (sg * ((ak * (x0 + (float)U) + tk) + ck) < 0.0f)) --U;
-                        hi = U;
+                    if (dir > 0.0f || dir < 0.0f) {
+                        // accepted cells are a half-line: col >= boundary (dir > 0, step +1) or col <= boundary (dir < 0,
+                        // step -1).  One code path for both directions, so lanes of differently oriented edges do not
+                        // diverge: guess analytically, walk outwards while the cell before is still accepted, then
+                        // inwards while the cell itself is rejected -- the real predicate decides, the guess only seeds.
+                        if (hi >= lo) {
+                            const int st = dir > 0.0f ? 1 : -1;
+                            const float q = __fdividef(-(tk + ck), ak) - x0;
+                            int g = st > 0 ? __float2int_ru(q) : __float2int_rd(q);
+                            g = min(max(g, lo - (st < 0)), hi + (st > 0));
+                            const unsigned span = (unsigned)(hi - lo);
+                            while ((unsigned)(g - st - lo) <= span && !(sg * ((ak * (x0 + (float)(g - st)) + tk) + ck) < 0.0f)) g -= st;
+                            while ((unsigned)(g - lo) <= span && (sg * ((ak * (x0 + (float)g) + tk) + ck) < 0.0f)) g += st;
+                            if (st > 0) lo = g; else hi = g;
+                        }
                     } else if (sg * ((ak * x0 + tk) + ck) < 0.0f) { // constant along the row (ak == 0 or NaN): all or nothing
                         hi = lo - 1;
                     }

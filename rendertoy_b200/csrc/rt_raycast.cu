@@ -362,7 +362,9 @@ __device__ __forceinline__ void clear_band(const TraceArgs &a, int band)
 // a node while the warp votes (+15 %: the loop is issue-bound, not latency-bound); 64- or 32-thread blocks (+5 - 10 %);
 // the packet walk over the 3-D nodes with per-lane slab tests (100k triangles: 228 vs 253 us per-lane, but 1M: 512 vs 407 us,
 // sub-pixel triangles leave nothing for a tile to share -- and below ~256k triangles the screen-space packets win anyway);
-// a multiplicative permutation of the launch order, to keep the object's expensive tiles out of the kernel's tail (+-0 %).
+// a multiplicative permutation of the launch order, to keep the object's expensive tiles out of the kernel's tail (+-0 %);
+// 32x4-pixel strips per block with colours swapped through shared memory so that every warp stores whole 128-byte rows,
+// meant for frames in another GPU's memory (-5 % locally, +-0 % at N=4 over NVLink: store width is not what binds rank 0).
 template <int MODE, bool STATS, bool FMA, bool VIEW>
 __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const TraceArgs a)
 {

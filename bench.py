@@ -161,8 +161,7 @@ def bench_raycast(args, rank, world):
     store = parallel.FrameStore(2 * n_frames, RAY_W, RAY_H) if (world > 1 and args.gather == "peer") else None
     fused = store is not None and store.ok
     if fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
-        remote = rank != 0 and os.environ.get("RENDERTOY_B200_ROW_STORES", "1") != "0"   # whole-row stores into rank 0's HBM
-        targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k), remote=remote) for k in my_frames] for b in range(2)]
+        targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k)) for k in my_frames] for b in range(2)]
         targets = targets2[0]
         local = gathered = None
     else:

@@ -117,8 +117,6 @@ int rt_texture_destroy(uint64_t handle);
  * hits: the closest hit is defined by the exact triangle test alone. */
 #define RT_BVH_LBVH 0
 #define RT_BVH_PLOC 1
-#define RT_RAYCAST_FAST_SLAB 1
-#define RT_RAYCAST_ROW_STORES 2
 int64_t rt_bvh_node_bytes(int64_t n_triangles);    /* bytes of d_nodes   (64 B inner nodes)            */
 int64_t rt_bvh_tri_bytes(int64_t n_triangles);     /* bytes of d_tris    (48 B leaf triangles, sorted) */
 int64_t rt_bvh_scratch_bytes(int64_t n_triangles); /* bytes of d_scratch (build only)                  */
@@ -140,11 +138,8 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * shading; d_pos4 / tex_handle are only needed for lesson09.  d_stats: NULL, or 3 x uint64 that an instrumented
  * build of the kernel ADDS {inner-node visits, triangle tests, rays} to (for the roofline report; slower).
  * cull_rect: NULL, or 4 ints {x0, y0, x1, y1} (inclusive, frame pixels): a conservative screen-space bound of the
- * scene the caller computed; pixels outside are written as misses without tracing.  flags: RT_RAYCAST_FAST_SLAB lets
- * the 3-D box tests use the FMA form (caller guarantees the origin is within 16 scene extents of the scene);
- * RT_RAYCAST_ROW_STORES makes every warp store whole 128-byte rows of the frame (blocks own 32x4-pixel strips and swap
- * colours through shared memory) -- for d_bgra in another GPU's memory, where 32-byte stores waste NVLink packets;
- * 4-5 % slower on a local target.
+ * scene the caller computed; pixels outside are written as misses without tracing.  fast_slab: non-zero lets the
+ * box tests use the FMA form (caller guarantees the origin is within 16 scene extents of the scene).
  * d_view_nodes: NULL, or rt_raycast_view_node_bytes(n_triangles) of 16-byte aligned device scratch: the call then
  * first projects every BVH node into this camera's screen space (one small kernel) and the traversal tests pixels
  * against screen rectangles instead of rays against boxes -- same hits, fewer instructions per node.  The scratch is
@@ -153,7 +148,7 @@ int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
-                       int64_t bgra_pitch_px, void *d_stats, const int *cull_rect, int flags,
+                       int64_t bgra_pitch_px, void *d_stats, const int *cull_rect, int fast_slab,
                        void *d_view_nodes, void *stream);
 
 /* ---- run-time kernels  (rendering/_core.py:247-299: kernel_main / build_kernel_main, one OpenCL program built at

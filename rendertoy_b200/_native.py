@@ -10,7 +10,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENDERTOY_B200_LIB") or os.path.join(HERE, "librendertoy_b200.so")   # override: A/B builds
 
 BVH_LBVH, BVH_PLOC = 0, 1
-RAYCAST_FAST_SLAB, RAYCAST_ROW_STORES = 1, 2
 SHADER_LESSON08 = 8
 SHADER_LESSON09 = 9
 NO_PRIMITIVE = 0xFFFFFFFF

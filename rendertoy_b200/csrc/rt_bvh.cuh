@@ -18,9 +18,3 @@ struct __align__(16) RtBvhTri { float4 v0, e1, e2; };
 #define RT_BVH_PLOC 1
 #endif
 #define RT_BVH_MAX_HEIGHT 64
-
-// rt_raycast_primary's `flags` (include/rendertoy_b200.h)
-#ifndef RT_RAYCAST_FAST_SLAB
-#define RT_RAYCAST_FAST_SLAB 1
-#define RT_RAYCAST_ROW_STORES 2
-#endif

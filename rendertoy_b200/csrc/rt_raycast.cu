@@ -22,8 +22,7 @@ namespace {
 #define RT_RAYCAST_MINB 12 // 40 registers: 48 of 64 warps resident (2 % over the unconstrained 46-register build)
 #endif
 constexpr int TB = RT_RAYCAST_TB;   // threads per block
-// tiles of one block: 2 x 2 (16 x 8 pixels), or with TraceArgs::strip 4 x 1 (32 x 4 pixels, see raycast_kernel)
-constexpr int TILES_BX = TB >= 64 ? 2 : 1, TILES_BY = TB / 32 / TILES_BX;
+constexpr int TILES_BX = TB >= 64 ? 2 : 1, TILES_BY = TB / 32 / TILES_BX; // tiles of one block
 constexpr int STACK = 64; // Karras tree depth <= 64 (32 key bits + index tiebreak), one pending sibling per level
 // The per-lane stack lives in local memory (L1-resident, only the touched depth is ever cached).  Measured on B200
 // against a [depth][thread] shared-memory stack: 332 vs 374 us per 4K frame -- the 32 KB of shared memory per CTA
@@ -132,7 +131,6 @@ struct TraceArgs {
     int tex_w, tex_h;
     int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
     int tt[4];     // primary mode: traced tile rectangle {tile x0, tile y0, tiles wide, tiles high} (8x4-pixel tiles of the rect)
-    int strip;        // primary mode: 4x1-tile blocks with whole-row colour stores (peer-memory targets)
     int trace_blocks; // primary mode: blocks [0, trace_blocks) trace 2x2 tiles each, the rest clear
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
@@ -372,44 +370,27 @@ __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const Trac
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (MODE) {
         if ((int)blockIdx.x >= a.trace_blocks) { clear_band(a, (int)blockIdx.x - a.trace_blocks); return; }
-        const bool strip_mode = TB == 128 && a.strip != 0;
-        const int tbx = strip_mode ? 4 : TILES_BX, tby = strip_mode ? 1 : TILES_BY;
-        const int bw = (a.tt[2] + tbx - 1) / tbx;
-        const int tx = a.tt[0] + tbx * ((int)blockIdx.x % bw) + wid % tbx, ty = a.tt[1] + tby * ((int)blockIdx.x / bw) + wid / tbx;
-        const bool tile_ok = tx < a.tt[0] + a.tt[2] && ty < a.tt[1] + a.tt[3];
-        if (!strip_mode && !tile_ok) return;
+        const int bw = (a.tt[2] + TILES_BX - 1) / TILES_BX;
+        const int tx = a.tt[0] + TILES_BX * ((int)blockIdx.x % bw) + wid % TILES_BX, ty = a.tt[1] + TILES_BY * ((int)blockIdx.x / bw) + wid / TILES_BX;
+        if (tx >= a.tt[0] + a.tt[2] || ty >= a.tt[1] + a.tt[3]) return;
         const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
-        const bool live = tile_ok && lx < a.w && ly < a.h;
+        const bool live = lx < a.w && ly < a.h;
         const float sx = ((float)(a.x0 + lx) + 0.5f) * (2.0f / (float)a.width) - 1.0f;
         const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * (2.0f / (float)a.height);
         const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
         const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
         const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
         Hit h;
-        h.t = INFINITY; h.u = 0.0f; h.v = 0.0f; h.id = 0xFFFFFFFFu;
         if (VIEW) {
             __shared__ int4 wstacks[TB / 32][STACK];
             h = trace_view_packet<STATS>(a, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstacks[wid]);
-        } else if (live) {
+            if (!live) return;
+        } else {
+            if (!live) return;
             h = trace<STATS, FMA>(a, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, stack);
         }
-        if (live && a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
-        if (!a.bgra) return;
-        const uint32_t colour = live ? shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h) : 0u;
-        if (!strip_mode) {
-            if (live) a.bgra[(long long)ly * a.pitch_px + lx] = colour;
-            return;
-        }
-        // 8x4 tiles make 32-byte row segments; with the frame in another GPU's memory those are NVLink packets that
-        // are mostly header.  In strip mode (RT_RAYCAST_ROW_STORES, for peer-memory targets) the block's four tiles sit
-        // side by side as a 32x4-pixel strip and swap colours so that warp w stores row w as one 128-byte line.  On a
-        // local target this costs 4-5 % (a barrier, flatter blocks), so it is the caller's choice.
-        __shared__ uint32_t strip[4][32];
-        strip[lane >> 3][wid * 8 + (lane & 7)] = colour; // [row][column of the strip]
-        __syncthreads();
-        const int sx_px = (tx - wid) * 8 + lane, sy_px = ty * 4 + wid; // this lane's pixel of row `wid` (ty is the same for the whole block)
-        const bool stored = (tx - wid) + (lane >> 3) < a.tt[0] + a.tt[2] && sx_px < a.w && sy_px < a.h;
-        if (stored) a.bgra[(long long)sy_px * a.pitch_px + sx_px] = strip[wid][lane];
+        if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
+        if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
     } else {
         const long long r = ((long long)blockIdx.x * (TB / 32) + wid) * 32 + lane;
         if (r >= a.n_rays) return;
@@ -430,8 +411,7 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
         const int cy1 = (a.cull[3] < a.y0 + a.h - 1 ? a.cull[3] : a.y0 + a.h - 1) - a.y0;
         if (cx1 < cx0 || cy1 < cy0) { a.tt[0] = a.tt[1] = a.tt[2] = a.tt[3] = 0; }
         else { a.tt[0] = cx0 >> 3; a.tt[1] = cy0 >> 2; a.tt[2] = (cx1 >> 3) - a.tt[0] + 1; a.tt[3] = (cy1 >> 2) - a.tt[1] + 1; }
-        const int tbx = (TB == 128 && a.strip) ? 4 : TILES_BX, tby = (TB == 128 && a.strip) ? 1 : TILES_BY;
-        a.trace_blocks = ((a.tt[2] + tbx - 1) / tbx) * ((a.tt[3] + tby - 1) / tby);
+        a.trace_blocks = ((a.tt[2] + TILES_BX - 1) / TILES_BX) * ((a.tt[3] + TILES_BY - 1) / TILES_BY);
         const bool all_traced = a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
         blocks = (long long)a.trace_blocks + (all_traced ? 0 : (a.h + 3) >> 2);
     } else {
@@ -504,7 +484,7 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4, const void *d_nrm4,
                        const int32_t *d_indices, const float *camera, int width, int height, int x0, int y0, int w, int h, int shader,
                        uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_stats,
-                       const int *cull_rect, int flags, void *d_view_nodes, void *stream)
+                       const int *cull_rect, int fast_slab, void *d_view_nodes, void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
     RT_REQUIRE(camera, "camera");
@@ -514,8 +494,6 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     RT_REQUIRE(d_hits || d_bgra, "at least one output");
     if (w == 0 || h == 0) return RT_OK;
     TraceArgs a = {};
-    const int fast_slab = flags & RT_RAYCAST_FAST_SLAB;
-    a.strip = (flags & RT_RAYCAST_ROW_STORES) ? 1 : 0;
     a.nodes = (const RtBvhNode *)d_nodes; a.tris = (const RtBvhTri *)d_tris;
     for (int i = 0; i < 12; ++i) a.cam[i] = camera[i];
     a.width = width; a.height = height; a.x0 = x0; a.y0 = y0; a.w = w; a.h = h;

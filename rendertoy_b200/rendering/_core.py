@@ -397,10 +397,9 @@ class Image:
     """2-D image in linear device memory, row-major, `components` channels per pixel.  For the RGBA dtype the
     bytes are B,G,R,A (CL_BGRA UNORM8) exactly as the reference's render target (rendering/_core.py:340)."""
 
-    def __init__(self, width, height, dtype, memory=None, remote=False):
+    def __init__(self, width, height, dtype, memory=None):
         """memory: optional torch uint8 tensor (width*height*pixel bytes) to use instead of a fresh allocation --
-        e.g. one frame of a parallel.FrameStore, which may live on another GPU of the node (then pass remote=True:
-        renderers pick the store pattern that suits NVLink)."""
+        e.g. one frame of a parallel.FrameStore, which may live on another GPU of the node."""
         dtype = np.dtype(dtype) if not isinstance(dtype, np.dtype) else dtype
         assert dtype in _IMAGE_FORMATS, "Unsupported dtype for image format"
         self.width, self.height, self.depth = int(width), int(height), 0
@@ -410,7 +409,6 @@ class Image:
         nbytes = self.width * self.height * item
         self._buffer = DeviceBuffer(_Storage(nbytes, tensor=memory), 0, (self.height, self.width, self.components),
                                     np.dtype(self.channel_dtype))
-        self.remote = bool(remote)
         self._pending_clear = None   # rgba of a clear() not yet executed (BGRA8 targets only)
 
     @property

@@ -195,15 +195,14 @@ class Raycaster:
 
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
-               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True, view_nodes=None, row_stores=None):
+               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True, view_nodes=None):
         """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
         shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
         hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
         hits are wanted (then frame_size=(W, H) is required).  stats: optional int64[3] tensor; the instrumented kernel
         adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds.
         view_nodes: project the BVH into this camera's screen space first and traverse that (default: yes up to
-        VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself).  row_stores: store whole
-        128-byte rows of the frame (default: only when the render target lives in another GPU's memory, `Image.remote`)."""
+        VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself)."""
         if render_target is not None:
             W, H = render_target.width, render_target.height
         else:
@@ -227,11 +226,7 @@ class Raycaster:
             if r is not None:
                 import ctypes
                 rect_c = (ctypes.c_int * 4)(*r)
-        flags = _native.RAYCAST_FAST_SLAB if float(np.abs(cam32[0:3]).max()) <= 16.0 * self.scene_extent else 0
-        if row_stores is None:
-            row_stores = render_target is not None and getattr(render_target, "remote", False)
-        if row_stores:
-            flags |= _native.RAYCAST_ROW_STORES
+        fast_slab = int(float(np.abs(cam32[0:3]).max()) <= 16.0 * self.scene_extent)
         if view_nodes is None:
             view_nodes = self.n_triangles <= VIEW_NODES_MAX_TRIANGLES
         vn_ptr = None
@@ -245,6 +240,6 @@ class Raycaster:
                      self.nrm4.data_ptr(), self._idx_ptr(),
                      _native.float_array_from_bytes(cam32.view(np.uint8), 12),
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
-                     None if stats is None else stats.data_ptr(), rect_c, flags, vn_ptr, stream_ptr())
+                     None if stats is None else stats.data_ptr(), rect_c, fast_slab, vn_ptr, stream_ptr())
         if render_target is not None:
             render_target._buffer.device_written()

@@ -331,24 +331,3 @@ def test_ploc_builder_trees_and_hits(ren, oracle):
         ref = oracle.raycast_brute(np.ascontiguousarray(rows), oracle.primary_rays(cam, w, h))
         _check(a.view(np.float32), ref, label)
         print(f"{label}: n={rows.shape[0] // 3} heights ploc {hp} lbvh {hl}, hit pixels {int((a[:, 1] != 0xFFFFFFFF).sum())}")
-
-
-def test_row_store_mode_writes_the_same_frame(ren, oracle):
-    """RT_RAYCAST_ROW_STORES (32x4-pixel strips, whole-row stores for peer-memory targets) against the default block shape:
-    identical BGRA8 frames and hit records, for full frames, odd sizes and sub-rectangles, with and without view nodes."""
-    from rendering._raycaster import Raycaster
-    rows = scenes.dragon(4_000)
-    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
-    for (w, h, rect) in [(640, 360, None), (333, 201, None), (640, 360, (37, 11, 401, 203)), (96, 64, (5, 6, 7, 9))]:
-        cam = _camera(ren, 6, 0.8, w, h)
-        for vn in (True, False):
-            frames, hits = [], []
-            for rs in (False, True):
-                target = ren.create_image2d(w, h, ren._core.RGBA)
-                ren.clear(target, (0.3, 0.2, 0.1, 1.0))
-                rw, rh = (rect[2], rect[3]) if rect else (w, h)
-                hh = torch.empty((rw * rh, 4), dtype=torch.float32, device="cuda")
-                rc.render(target, cam, rect=rect, hits=hh, view_nodes=vn, row_stores=rs)
-                frames.append(target.get().copy()); hits.append(hh.cpu().numpy().view(np.uint32))
-            assert np.array_equal(frames[0], frames[1]), f"{w}x{h} rect={rect} view_nodes={vn}: frames differ"
-            assert np.array_equal(hits[0], hits[1]), f"{w}x{h} rect={rect} view_nodes={vn}: hit records differ"

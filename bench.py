@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 N_TRIS = 100_000
 RAY_W, RAY_H = 3840, 2160
 RAS_W, RAS_H = 1920, 1080
-FRAMES_PER_RANK = 8
+FRAMES_PER_RANK = int(os.environ.get("RENDERTOY_B200_FRAMES_PER_RANK", "8"))
 ORBIT = 256  # World = rotate(2*pi*k/256, y)  
 
 METRIC_RAY = "Mrays/s closest-hit (dragon, 4K)"
@@ -133,6 +133,18 @@ def barrier_sync(world):
     torch.cuda.synchronize()
 
 
+def all_ranks(ms, world):
+    """every rank's value, in rank order (for the per-rank breakdown in the JSON line)"""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[dist.get_rank()] = ms
+        dist.all_reduce(t)
+        return [float(x) for x in t.cpu()]
+    return [ms]
+
+
 def max_over_ranks(ms, world):
     import torch
     import torch.distributed as dist
@@ -158,9 +170,21 @@ def bench_raycast(args, rank, world):
     rc = Raycaster([ren.Mesh(vb, None)])
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
-    store = parallel.FrameStore(2 * n_frames, RAY_W, RAY_H) if (world > 1 and args.gather == "peer") else None
-    fused = store is not None and store.ok
-    if fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
+    store = parallel.FrameStore(2 * n_frames, RAY_W, RAY_H) if (world > 1 and args.gather in ("peer", "copy")) else None
+    fused = store is not None and store.ok and args.gather == "peer"
+    pushed = store is not None and store.ok and args.gather == "copy"
+    if pushed:  # ranks != 0 render locally and a copy engine pushes each finished frame into rank 0's frame store while the
+        # next frame traces; rank 0 renders straight into the store
+        slots2 = [[store.frame(b * n_frames + k) for k in my_frames] for b in range(2)]
+        if rank == 0:
+            targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=m) for m in slots2[b]] for b in range(2)]
+            targets = targets2[0]
+        else:
+            targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
+        push_stream = torch.cuda.Stream()
+        rendered = [torch.cuda.Event() for _ in range(F)]
+        local = gathered = None
+    elif fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
         targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k)) for k in my_frames] for b in range(2)]
         targets = targets2[0]
         local = gathered = None
@@ -177,7 +201,7 @@ def bench_raycast(args, rank, world):
     main_stream = torch.cuda.current_stream()
 
     def step(s, timed_idx=None):
-        tg = targets2[s % 2] if fused else targets
+        tg = targets2[s % 2] if (fused or (pushed and rank == 0)) else targets
         if ray_streams is not None:
             for st in ray_streams:
                 st.wait_stream(main_stream)
@@ -189,14 +213,21 @@ def bench_raycast(args, rank, world):
             rc.render(tg[j], cams[s * n_frames + k])
             if timed_idx is not None:
                 ev[timed_idx * F + j][1].record()
+            if pushed and rank != 0:
+                rendered[j].record()
+                push_stream.wait_event(rendered[j])
+                with torch.cuda.stream(push_stream):
+                    slots2[s % 2][j].copy_(tg[j].buffer.tensor().view(torch.uint8).view(-1), non_blocking=True)
         if ray_streams is not None:
             torch.cuda.set_stream(main_stream)
             for st in ray_streams:
                 main_stream.wait_stream(st)
+        if pushed:
+            main_stream.wait_stream(push_stream)
         collect()
 
     def collect():   # the only collective: finished frames -> rank 0
-        if fused:
+        if fused or pushed:
             store.commit()
         elif world > 1:
             for j in range(F):
@@ -214,6 +245,7 @@ def bench_raycast(args, rank, world):
     e1.record()
     barrier_sync(world)
     clocks = sampler.result()
+    ms_ranks = all_ranks(e0.elapsed_time(e1), world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     rays_total = RAY_W * RAY_H * n_frames * args.steps
     value = rays_total / (ms * 1e-3) / 1e6
@@ -284,11 +316,14 @@ def bench_raycast(args, rank, world):
                    "frames_per_rank_per_step": F,
                    "partition": "frames k = rank (mod N); " + ("every rank's kernel stores its pixels straight into rank 0's frame store "
                                 "over NVLink (CUDA IPC peer memory, double-buffered), one stream-ordered 4-byte all-reduce per step" if fused else
+                                "ranks != 0 render locally and push each finished frame into rank 0's frame store (CUDA IPC peer memory, "
+                                "double-buffered) with an async device-to-device copy that overlaps the next frame; rank 0 renders in place; "
+                                "one stream-ordered 4-byte all-reduce per step" if pushed else
                                 "framebuffers gathered to rank 0 with NCCL send/recv" if world > 1 else "single GPU, no gather"),
                    "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
                          "L2-resident by design, as they are reused every frame",
                    "streams": f"frames alternate over {args.raycast_streams} CUDA streams" if ray_streams else "single stream",
-                   "bvh_build_excluded": True},
+                   "bvh_build_excluded": True, "timed_region_ms_per_rank": ms_ranks},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": ncu_traffic().get("raycast_kernel"), "peak_source": peak_src,
                      "kernel": "raycast_kernel<8> (+ project_kernel, same launch pair)", "kernel_ms": kernel_ms, "kernel_ms_alone": isolated_ms, "kernel_ms_overlapped_launch": launch_ms,
@@ -332,7 +367,7 @@ def bench_raster(args, rank, world, rows=None):
     F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
     my_frames = parallel.frame_indices(n_frames, rank, world)
     # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
-    store = parallel.FrameStore(2 * n_frames, RAS_W, RAS_H) if (world > 1 and args.gather == "peer") else None
+    store = parallel.FrameStore(2 * n_frames, RAS_W, RAS_H) if (world > 1 and args.gather != "nccl") else None
     fused = store is not None and store.ok
     rasters, rasters_b = [], []
     for j in range(F):
@@ -538,8 +573,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--raycast-streams", type=int, default=4, help="raycast frames of a step alternate over this many CUDA streams")
     ap.add_argument("--raster-streams", type=int, default=1, help="1: one CUDA stream per raster frame target (default), 0: single stream")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N>1: peer = kernels write into rank 0's IPC-mapped frame store (fused); nccl = send/recv gather")
+    ap.add_argument("--gather", default="copy", choices=["peer", "copy", "nccl"],
+                    help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
+                         "IPC-mapped frame store while the next frame traces (default: fastest from N=4 up); peer = the kernels store "
+                         "straight into that frame store over NVLink (fused); nccl = send/recv gather.  Raster frames: peer unless nccl")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

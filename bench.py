@@ -332,7 +332,7 @@ def bench_raycast(args, rank, world):
                                        "kernel_ms_overlapped_launch = CUDA events around each launch pair inside the timed region",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "HBM does not bind this kernel (BVH and its per-frame screen-space copy are L2-resident); the binding "
-                             "unit is the instruction issue rate (compares, votes, branches of the packet walk: ~67 % of issue "
+                             "unit is the instruction issue rate (compares, votes, branches of the packet walk: ~73 % of issue "
                              "slots busy in profiles/), see fp32 for the arithmetic it amounts to",
                      "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,

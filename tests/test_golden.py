@@ -69,3 +69,49 @@ def test_product_reproduces_reference_run(ren, path):
     assert np.array_equal(depth, z["depth"]), "depth bits differ from the reference run"
     diff = (raster.get_render_target().get() != z["bgra"]).any(axis=-1)
     assert not (diff & (z["tie"] == 0)).any(), "colour differs from the reference run outside depth ties"
+
+
+# ---- ray casting: no reference implementation exists (rendering/_raycaster.py:35-36 is `pass`), so the fixture comes from a
+# second, independent restatement of the definition in numpy float32 (tests/golden/make_raycast_golden.py)
+
+RAYCAST_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raycast_numpy_dragon300.npz")
+
+
+def _same_hits(t, ids, u, v, z, label):
+    assert np.array_equal(ids, z["ids"]), f"{label}: triangle ids differ on {int((ids != z['ids']).sum())} rays"
+    for name, a in (("t", t), ("u", u), ("v", v)):
+        assert np.array_equal(np.asarray(a, np.float32).view(np.uint32), z[name].view(np.uint32)), f"{label}: {name} bits differ"
+
+
+def test_oracle_reproduces_numpy_raycast():
+    import oracle
+    z = np.load(RAYCAST_GOLDEN)
+    w, h = int(z["width"]), int(z["height"])
+    rays = oracle.primary_rays(z["camera"], w, h)
+    t, ids, u, v = oracle.raycast_brute(z["rows"], rays)
+    _same_hits(t, ids, u, v, z, "brute force")
+    bvh = oracle.bvh_build(z["rows"])
+    tb, ib, ub, vb = oracle.bvh_raycast(bvh, rays)
+    oracle.bvh_free(bvh)
+    _same_hits(tb, ib, ub, vb, z, "cpu bvh")
+    assert np.array_equal(oracle.shade_hits(8, z["rows"], ids, u, v).reshape(h, w, 4), z["bgra"]), "Lambert BGRA8 differs"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("builder,view_nodes", [("ploc", True), ("lbvh", True), ("ploc", False)])
+def test_cuda_reproduces_numpy_raycast(ren, builder, view_nodes):
+    import torch
+    from rendering._raycaster import Raycaster
+    z = np.load(RAYCAST_GOLDEN)
+    w, h = int(z["width"]), int(z["height"])
+    rows = z["rows"]
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    rc = Raycaster([ren.Mesh(vb, None)], builder=builder)
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    hits = torch.empty((w * h, 4), dtype=torch.float32, device="cuda")
+    rc.render(target, z["camera"], hits=hits, view_nodes=view_nodes)
+    got = hits.cpu().numpy()
+    _same_hits(got[:, 0], got[:, 1].view(np.uint32), got[:, 2], got[:, 3], z, f"cuda {builder} view_nodes={view_nodes}")
+    assert np.array_equal(target.get(), z["bgra"]), "Lambert BGRA8 differs"

@@ -43,9 +43,11 @@ struct ProjectArgs {
     const RtBvhNode *nodes;
     ViewNode *vnodes;
     long long n_inner;
+    const RtBvhTri *tris;
     double minv[9]; // rows of [U V W]^-1
     double o[3];
     float pad_s;    // rectangle padding per unit of (1 + |s|)
+    float rowsum;   // largest absolute row sum of [U V W]^-1: how far a unit displacement in space can move (a, b, c)
 };
 
 __device__ __forceinline__ void project_child(const ProjectArgs &p, float lox, float hix, float loy, float hiy, float loz, float hiz, float4 &rect,
@@ -91,6 +93,40 @@ __device__ __forceinline__ void project_child(const ProjectArgs &p, float lox, f
     zmin = cmin * (1.0f - 64.0f * p.pad_s);
 }
 
+// A leaf's rectangle from the triangle itself: the box of a slanted triangle is mostly empty, and its projection more so.
+// The triangle the exact test sees is v0 + u e1 + v e2; what it can report as a hit lies within the same 3-D tolerance
+// the leaf boxes are padded with (read back here as box - vertex extent, doubled), which at depth c is a screen
+// displacement of at most r rowsum (1 + |s|) / (c - r rowsum).  The result is intersected with the box's rectangle.
+__device__ __forceinline__ void project_leaf(const ProjectArgs &p, int slot, float lox, float loy, float loz, float4 &rect, float &zmin)
+{
+    const float4 *tp = reinterpret_cast<const float4 *>(p.tris + slot);
+    const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+    const double P[3][3] = {{(double)v0.x, (double)v0.y, (double)v0.z},
+                            {(double)v0.x + (double)e1.x, (double)v0.y + (double)e1.y, (double)v0.z + (double)e1.z},
+                            {(double)v0.x + (double)e2.x, (double)v0.y + (double)e2.y, (double)v0.z + (double)e2.z}};
+    const double vminx = fmin(P[0][0], fmin(P[1][0], P[2][0])), vminy = fmin(P[0][1], fmin(P[1][1], P[2][1])),
+                 vminz = fmin(P[0][2], fmin(P[1][2], P[2][2]));
+    const float r3 = 2.0f * (float)fmax(vminx - (double)lox, fmax(vminy - (double)loy, vminz - (double)loz)); // ~2 x the box padding
+    float smin = INFINITY, smax = -INFINITY, tmin = INFINITY, tmax = -INFINITY, cmin = INFINITY;
+    bool bad = !(r3 >= 0.0f) || !(r3 < INFINITY);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double qx = P[k][0] - p.o[0], qy = P[k][1] - p.o[1], qz = P[k][2] - p.o[2];
+        const float af = (float)(p.minv[0] * qx + p.minv[1] * qy + p.minv[2] * qz), bf = (float)(p.minv[3] * qx + p.minv[4] * qy + p.minv[5] * qz),
+                    cf = (float)(p.minv[6] * qx + p.minv[7] * qy + p.minv[8] * qz);
+        const float s = af / cf, t = bf / cf;
+        smin = fminf(smin, s); smax = fmaxf(smax, s); tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+        cmin = fminf(cmin, cf);
+        bad = bad || !(fabsf(s) < INFINITY) || !(fabsf(t) < INFINITY) || !(fabsf(cf) < INFINITY);
+    }
+    const float reach = r3 * p.rowsum; // how far the tolerance moves (a, b, c)
+    if (bad || !(cmin > 4.0f * reach) || !(cmin > 0.0f)) return; // keep the box's rectangle
+    const float k = reach / (cmin - reach) * 1.0001f + p.pad_s;
+    rect.x = fmaxf(rect.x, smin - k * (1.0f + fabsf(smin))); rect.y = fminf(rect.y, smax + k * (1.0f + fabsf(smax)));
+    rect.z = fmaxf(rect.z, tmin - k * (1.0f + fabsf(tmin))); rect.w = fminf(rect.w, tmax + k * (1.0f + fabsf(tmax)));
+    zmin = fmaxf(zmin, (cmin - reach) * (1.0f - 64.0f * p.pad_s));
+}
+
 // One thread per inner node.  Padding: the traced direction is fl(fl(U sx + V sy) + W), off the exact U sx + V sy + W by
 // at most eps_d = 2^-22 (|U| |sx| + |V| |sy| + |W|) per component; through [U V W]^-1 that moves the ray's screen point by
 // <= rowsum |Minv| eps_d (1 + |s|) -- the host passes pad_s = 8 x that bound (about 3 % of a 4K pixel for the lesson
@@ -106,6 +142,10 @@ __global__ void __launch_bounds__(128) project_kernel(const ProjectArgs p)
     float z0, z1;
     project_child(p, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, v.r0, z0);
     project_child(p, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, v.r1, z1);
+    if (p.tris) {
+        if (n3.x < 0) project_leaf(p, ~n3.x, n0.x, n0.z, n2.x, v.r0, z0);
+        if (n3.y < 0 && n1.x <= n1.y) project_leaf(p, ~n3.y, n1.x, n1.z, n2.z, v.r1, z1);
+    }
     v.zc = make_float4(z0, z1, __int_as_float(n3.x), __int_as_float(n3.y));
     p.vnodes[i] = v;
 }
@@ -459,6 +499,7 @@ bool camera_inverse(const float *cam, ProjectArgs &p)
     const double pad = 8.0 * rowsum * dmax * 2.384185791015625e-7; // 8 x rowsum x 2^-22 dmax
     if (!(pad < 1e-3)) return false; // ill-conditioned basis: not worth it, walk the 3-D nodes
     p.pad_s = (float)pad;
+    p.rowsum = (float)(rowsum * 1.000001);
     p.o[0] = cam[0]; p.o[1] = cam[1]; p.o[2] = cam[2];
     return true;
 }
@@ -507,6 +548,7 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
         ProjectArgs p = {};
         if (camera_inverse(camera, p)) {
             p.nodes = a.nodes; p.vnodes = (ViewNode *)d_view_nodes; p.n_inner = n_triangles > 1 ? n_triangles - 1 : 1;
+            p.tris = a.tris; // leaf rectangles from the triangles themselves (189 -> 169 us per cfg4 frame against box rectangles)
             project_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
             RT_CUDA(cudaGetLastError());
             a.vnodes = p.vnodes;

@@ -182,7 +182,9 @@ def bench_raycast(args, rank, world):
         else:
             targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
         push_stream = torch.cuda.Stream()
+        push_ptr = push_stream.cuda_stream
         rendered = [torch.cuda.Event() for _ in range(F)]
+        local_ptrs = [t.ptr for t in targets] if rank != 0 else None
         local = gathered = None
     elif fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
         targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k)) for k in my_frames] for b in range(2)]
@@ -210,14 +212,14 @@ def bench_raycast(args, rank, world):
                 torch.cuda.set_stream(ray_streams[j % len(ray_streams)])
             if timed_idx is not None:
                 ev[timed_idx * F + j][0].record()
-            rc.render(tg[j], cams[s * n_frames + k])
+            content = rc.render(tg[j], cams[s * n_frames + k])
             if timed_idx is not None:
                 ev[timed_idx * F + j][1].record()
             if pushed and rank != 0:
+                # the frame is the clear colour outside `content` (the scene's projected bounds): only that rect travels
                 rendered[j].record()
                 push_stream.wait_event(rendered[j])
-                with torch.cuda.stream(push_stream):
-                    slots2[s % 2][j].copy_(tg[j].buffer.tensor().view(torch.uint8).view(-1), non_blocking=True)
+                pushed_bytes[0] += store.push((s % 2) * n_frames + k, local_ptrs[j], content if args.sparse else full_rect, push_ptr)
         if ray_streams is not None:
             torch.cuda.set_stream(main_stream)
             for st in ray_streams:
@@ -225,6 +227,9 @@ def bench_raycast(args, rank, world):
         if pushed:
             main_stream.wait_stream(push_stream)
         collect()
+
+    full_rect = (0, 0, RAY_W - 1, RAY_H - 1)
+    pushed_bytes = [0]
 
     def collect():   # the only collective: finished frames -> rank 0
         if fused or pushed:
@@ -238,6 +243,7 @@ def bench_raycast(args, rank, world):
         step(s)
     sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
     barrier_sync(world)
+    pushed_bytes[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
@@ -245,6 +251,21 @@ def bench_raycast(args, rank, world):
     e1.record()
     barrier_sync(world)
     clocks = sampler.result()
+    # untimed check of the gather: every rank compares the frames of the last step it rendered locally with what now
+    # sits in its slots of rank 0's frame store (read back over NVLink), bit for bit
+    gather_ok = None
+    if pushed:
+        s_last = args.warmup + args.steps - 1
+        ok = 1
+        if rank != 0:
+            for j, k in enumerate(my_frames):
+                slot = store.frame((s_last % 2) * n_frames + k).view(torch.int32)
+                ok &= int(torch.equal(slot, targets[j].buffer.tensor().view(torch.int32).view(-1)))
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+        assert gather_ok, "frames in rank 0's frame store differ from the frames the ranks rendered"
+    push_bytes_step = all_ranks(pushed_bytes[0] / max(args.steps, 1), world)
     ms_ranks = all_ranks(e0.elapsed_time(e1), world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     rays_total = RAY_W * RAY_H * n_frames * args.steps
@@ -267,10 +288,11 @@ def bench_raycast(args, rank, world):
     nodes, tests, rays = (int(x) for x in stats.cpu())
 
     # ---- e2e: public API, host inputs, every frame read back to pinned host memory
-    host = [torch.empty((RAY_H, RAY_W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    host = [torch.zeros((RAY_H, RAY_W), dtype=torch.int32).pin_memory() for _ in range(2)]   # cleared, like the frames
     copy_stream = torch.cuda.Stream()
+    copy_ptr = copy_stream.cuda_stream
     done = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
+    reader = parallel.SparseFrameCopier(RAY_W, RAY_H)
     from rendertoy_b200 import scenes
     from rendering._raycaster import camera_frame
 
@@ -282,16 +304,18 @@ def bench_raycast(args, rank, world):
         for j, k in enumerate(my_frames):
             world_m, view, proj = scenes.lesson_camera(ren, 6, orbit_t(s * n_frames + k), RAY_W, RAY_H)   # host inputs
             cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world_m, dtype=ren.float4x4))
-            rc.render(e2e_targets[j], cam)
+            content = rc.render(e2e_targets[j], cam)
             done[j % 2].record()
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[j % 2])
-                host[j % 2].copy_(e2e_targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W), non_blocking=True)
+            copy_stream.wait_event(done[j % 2])
+            # the frame is the clear colour outside `content`, and so is the (initially cleared) host frame outside the
+            # content of the frame it held before: one pitched D2H copy of the union makes the host frame complete
+            reader.copy(j % 2, host[j % 2].data_ptr(), e2e_targets[j].ptr, content if args.sparse_readback else full_rect, copy_ptr)
         torch.cuda.current_stream().wait_stream(copy_stream)
 
     e2e_step(0)
     barrier_sync(world)
     k_e2e = max(2, min(args.steps, 5))
+    reader.bytes_moved = 0
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for s in range(k_e2e):
@@ -299,6 +323,10 @@ def bench_raycast(args, rank, world):
     g1.record()
     barrier_sync(world)
     e2e_ms = max_over_ranks(g0.elapsed_time(g1), world)
+    # untimed check: the host frame that received the last frame is that frame, every pixel
+    j_last = F - 1
+    e2e_ok = bool(torch.equal(host[j_last % 2], e2e_targets[j_last].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W).cpu()))
+    assert e2e_ok, "sparse read-back: the host frame differs from the device frame"
     e2e_value = RAY_W * RAY_H * n_frames * k_e2e / (e2e_ms * 1e-3) / 1e6
 
     hbm_peak, peak_src = peaks()
@@ -317,13 +345,18 @@ def bench_raycast(args, rank, world):
                    "partition": "frames k = rank (mod N); " + ("every rank's kernel stores its pixels straight into rank 0's frame store "
                                 "over NVLink (CUDA IPC peer memory, double-buffered), one stream-ordered 4-byte all-reduce per step" if fused else
                                 "ranks != 0 render locally and push each finished frame into rank 0's frame store (CUDA IPC peer memory, "
-                                "double-buffered) with an async device-to-device copy that overlaps the next frame; rank 0 renders in place; "
-                                "one stream-ordered 4-byte all-reduce per step" if pushed else
+                                "double-buffered, cleared at start) with an async pitched copy-engine transfer that overlaps the next frame"
+                                + ("; only the pixel rect that can differ from the slot's content travels (union of the scene's projected "
+                                   "bounds of this frame and of the slot's previous frame: the frame is the clear colour elsewhere)" if args.sparse else "")
+                                + "; rank 0 renders in place; one stream-ordered 4-byte all-reduce per step" if pushed else
                                 "framebuffers gathered to rank 0 with NCCL send/recv" if world > 1 else "single GPU, no gather"),
                    "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
                          "L2-resident by design, as they are reused every frame",
                    "streams": f"frames alternate over {args.raycast_streams} CUDA streams" if ray_streams else "single stream",
-                   "bvh_build_excluded": True, "timed_region_ms_per_rank": ms_ranks},
+                   "bvh_build_excluded": True, "timed_region_ms_per_rank": ms_ranks,
+                   **({"gather_verified": "every rank's locally rendered frames of the last step == its slots of rank 0's frame store, bit for bit",
+                       "gather_bytes_per_step_per_rank": push_bytes_step, "full_frame_bytes_per_step_per_rank": 4 * RAY_W * RAY_H * F}
+                      if gather_ok else {})},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": ncu_traffic().get("raycast_kernel"), "peak_source": peak_src,
                      "kernel": "raycast_kernel<8> (+ project_kernel, same launch pair)", "kernel_ms": kernel_ms, "kernel_ms_alone": isolated_ms, "kernel_ms_overlapped_launch": launch_ms,
@@ -341,9 +374,13 @@ def bench_raycast(args, rank, world):
                               "flop_model": "per voting lane: 10 float compares per inner node (two screen rectangles + depth bound "
                                             "each) + 45 flop per Moller-Trumbore test; peak counts FMA as 2 flop, this kernel is "
                                             "compiled -fmad=false for bit-exact parity"}},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": 4 * RAY_W * RAY_H * F,
-                "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async D2H of the "
-                                        "33 MB BGRA8 frame into pinned memory (PCIe-bound); every rank reads back its own frames"},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": reader.bytes_moved // k_e2e,
+                "frame_bytes_per_step": 4 * RAY_W * RAY_H * F, "readback_verified": e2e_ok,
+                "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async pitched D2H copy into a "
+                                        "pinned, initially cleared host frame" + (" of the pixel rect that can differ from the clear colour (union "
+                                        "of the scene's projected bounds of this frame and of the frame the host buffer held before); the host "
+                                        "frame is complete and checked against the device frame after the timed region" if args.sparse_readback
+                                        else " of the whole 33 MB frame") + "; every rank reads back its own frames"},
         "gpu_launches": 2 * F * args.steps, "clocks": clocks,   # project_kernel + raycast_kernel per frame
     }
     return out, rows
@@ -573,6 +610,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--raycast-streams", type=int, default=4, help="raycast frames of a step alternate over this many CUDA streams")
     ap.add_argument("--raster-streams", type=int, default=1, help="1: one CUDA stream per raster frame target (default), 0: single stream")
+    ap.add_argument("--dense-gather", dest="sparse", action="store_false",
+                    help="--gather copy: push whole frames instead of the rect that can differ from the clear colour")
+    ap.add_argument("--dense-readback", dest="sparse_readback", action="store_false",
+                    help="e2e: read whole ray-cast frames back instead of the rect that can differ from the clear colour")
     ap.add_argument("--gather", default="copy", choices=["peer", "copy", "nccl"],
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
                          "IPC-mapped frame store while the next frame traces (default: fastest from N=4 up); peer = the kernels store "

@@ -145,6 +145,14 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * against screen rectangles instead of rays against boxes -- same hits, fewer instructions per node.  The scratch is
  * per call: concurrent calls on different streams need different buffers. */
 int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
+/* Host only, no device work: the cull_rect for rt_raycast_primary -- conservative inclusive pixel rect of the scene box
+ * [lo, hi] (3 doubles each) under `camera`, projected corners +- 2 px clamped to the frame.  Returns 1 and fills rect[4],
+ * or 0 when there is no usable bound (box reaches the eye plane, singular camera basis, non-finite data): pass NULL then. */
+/* Host only, no device work: the 12-float `camera` of rt_raycast_primary ({origin, U, V, W}, model space) from the
+ * reference's View / Proj / World matrices (16 floats each, row-major, row-vector convention of rendering/_core.py:528-548;
+ * world16 may be NULL).  Returns 1, or 0 for a singular view rotation / world matrix or non-finite data. */
+int rt_camera_frame(const float *view16, const float *proj16, const float *world16, float *out12);
+int rt_raycast_screen_bounds(const float *camera, const double *lo, const double *hi, int width, int height, int *rect);
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
@@ -170,6 +178,13 @@ int rt_peer_free(void *d_ptr);
 int rt_peer_export(const void *d_ptr, void *handle64);
 int rt_peer_open(const void *handle64, void **out_d_ptr);
 int rt_peer_close(void *d_ptr);
+/* The store starts cleared (rt_peer_alloc zero-fills it).  A ray-cast frame differs from the clear colour only inside the
+ * scene's projected bounds, so a rank that rendered locally moves just that pixel rectangle (`rows` rows of `width_bytes`,
+ * row pitches in bytes) into its slot of the store, or into a pinned host frame for the read-back (the reference side:
+ * pyopencl enqueue_copy(queue, array, image, origin, region)): one pitched copy-engine transfer on `stream`; either
+ * pointer may be local device, peer-mapped device or pinned host memory. */
+int rt_copy_rect(void *d_dst, int64_t dst_pitch_bytes, const void *d_src, int64_t src_pitch_bytes, int64_t width_bytes,
+                      int64_t rows, void *stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
                                      _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),
     "rt_raycast_view_node_bytes": (_I64, [_I64]),
+    "rt_camera_frame": (C.c_int, [_FP, _FP, _FP, _FP]),
+    "rt_raycast_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),
     "rt_dsl_launch": (C.c_int, [_U64, C.c_char_p, _I64, C.POINTER(_VP), _VP]),
     "rt_dsl_unload": (C.c_int, [_U64]),
@@ -44,6 +46,7 @@ SIGNATURES = {
     "rt_peer_export": (C.c_int, [_VP, _VP]),
     "rt_peer_open": (C.c_int, [_VP, C.POINTER(_VP)]),
     "rt_peer_close": (C.c_int, [_VP]),
+    "rt_copy_rect": (C.c_int, [_VP, _I64, _VP, _I64, _I64, _I64, _VP]),
     "rt_raster_points_scratch_bytes": (_I64, [_I64]),
     "rt_raster_draw_points": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, _VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),

@@ -13,6 +13,8 @@ int rt_peer_alloc(int64_t bytes, void **out_d_ptr)
 {
     RT_REQUIRE(bytes > 0 && out_d_ptr, "size / out pointer");
     RT_CUDA(cudaMalloc(out_d_ptr, (size_t)bytes));
+    RT_CUDA(cudaMemset(*out_d_ptr, 0, (size_t)bytes)); // a cleared frame store: rt_copy_rect pushes only what can differ from it
+    RT_CUDA(cudaDeviceSynchronize());                  // ... and cleared before the handle leaves this process
     return RT_OK;
 }
 
@@ -44,6 +46,24 @@ int rt_peer_open(const void *handle64, void **out_d_ptr)
 int rt_peer_close(void *d_ptr)
 {
     if (d_ptr) RT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RT_OK;
+}
+
+// Sparse frame movement: a ray-cast frame differs from the clear colour only inside the scene's projected bounds
+// (Raycaster.screen_bounds, a quarter of the dragon's 4K frame), so only that pixel rectangle -- `rows` rows of
+// `width_bytes`, row pitches in bytes -- has to travel: from a rank's local frame into its slot of rank 0's frame store
+// (peer-mapped, over NVLink) while its SMs trace the next frame, or into a pinned host frame (the read-back; pyopencl's
+// enqueue_copy(queue, array, image, origin, region) on the reference side).  ONE pitched copy-engine transfer on `stream`;
+// either side may be local device, peer-mapped device or pinned host memory (cudaMemcpyDefault).
+int rt_copy_rect(void *d_dst, int64_t dst_pitch_bytes, const void *d_src, int64_t src_pitch_bytes, int64_t width_bytes, int64_t rows,
+                      void *stream)
+{
+    RT_REQUIRE(width_bytes >= 0 && rows >= 0, "rectangle size");
+    if (width_bytes == 0 || rows == 0) return RT_OK;
+    RT_REQUIRE(d_dst && d_src, "source / destination");
+    RT_REQUIRE(dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes, "row pitch smaller than the row");
+    RT_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)dst_pitch_bytes, d_src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)rows,
+                              cudaMemcpyDefault, (cudaStream_t)stream));
     return RT_OK;
 }
 

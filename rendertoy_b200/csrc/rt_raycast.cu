@@ -565,6 +565,102 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     return launch_trace<8>(a, fast_slab != 0, (cudaStream_t)stream);
 }
 
+// Host only (no device work): {origin, U, V, W} (12 floats, model space) of the reference's camera convention
+// (rendering/_core.py:528-548, row vectors: p_clip = ((p World) View) Proj, left-handed, w = z_view): the pixel centre with
+// NDC coordinates (sx, sy) looks along U sx + V sy + W.  View = [R | 0; -eye R | 1] with the camera axes as COLUMNS of R,
+// Proj scales x, y by proj[0][0], proj[1][1].  With a World matrix the frame is carried into model space with World^-1
+// (general 4x4 inverse by cofactors, so scaled / sheared worlds work too).  All arithmetic in double, one rounding to float.
+// Returns 1, or 0 when R or World is singular or the data is not finite.  A tutorial frame calls this once per frame; numpy
+// needs ~140 us for the same arithmetic (two LAPACK inversions of tiny matrices), which is more than the 4K frame takes.
+int rt_camera_frame(const float *view16, const float *proj16, const float *world16, float *out12)
+{
+    if (!view16 || !proj16 || !out12) return 0;
+    double r[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[i][j] = view16[4 * i + j];
+    // inverse of R by cofactors
+    const double c00 = r[1][1] * r[2][2] - r[1][2] * r[2][1], c01 = r[1][2] * r[2][0] - r[1][0] * r[2][2], c02 = r[1][0] * r[2][1] - r[1][1] * r[2][0];
+    const double det = r[0][0] * c00 + r[0][1] * c01 + r[0][2] * c02;
+    if (!(det != 0.0) || !(det - det == 0.0)) return 0;
+    const double ri[3][3] = {{c00 / det, (r[0][2] * r[2][1] - r[0][1] * r[2][2]) / det, (r[0][1] * r[1][2] - r[0][2] * r[1][1]) / det},
+                             {c01 / det, (r[0][0] * r[2][2] - r[0][2] * r[2][0]) / det, (r[0][2] * r[1][0] - r[0][0] * r[1][2]) / det},
+                             {c02 / det, (r[0][1] * r[2][0] - r[0][0] * r[2][1]) / det, (r[0][0] * r[1][1] - r[0][1] * r[1][0]) / det}};
+    const double t[3] = {view16[12], view16[13], view16[14]};
+    double v[4][4]; // rows: eye (w = 1), U, V, W (w = 0)
+    for (int j = 0; j < 3; ++j) v[0][j] = -(t[0] * ri[0][j] + t[1] * ri[1][j] + t[2] * ri[2][j]);
+    v[0][3] = 1.0;
+    const double ws = proj16[0], hs = proj16[5];
+    for (int j = 0; j < 3; ++j) { v[1][j] = r[j][0] / ws; v[2][j] = r[j][1] / hs; v[3][j] = r[j][2]; }
+    v[1][3] = v[2][3] = v[3][3] = 0.0;
+    if (world16) {
+        double m[16], inv[16];
+        for (int i = 0; i < 16; ++i) m[i] = world16[i];
+        inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+        inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+        inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+        inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+        inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+        inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+        inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+        inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+        inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+        inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+        inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+        inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+        inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+        inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+        inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+        inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+        const double d4 = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+        if (!(d4 != 0.0) || !(d4 - d4 == 0.0)) return 0;
+        for (int k = 0; k < 4; ++k) {
+            double o[3];
+            for (int j = 0; j < 3; ++j) o[j] = (v[k][0] * inv[j] + v[k][1] * inv[4 + j] + v[k][2] * inv[8 + j] + v[k][3] * inv[12 + j]) / d4;
+            v[k][0] = o[0]; v[k][1] = o[1]; v[k][2] = o[2];
+        }
+    }
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 3; ++j) {
+            if (!(v[k][j] - v[k][j] == 0.0)) return 0;
+            out12[3 * k + j] = (float)v[k][j];
+        }
+    return 1;
+}
+
+// Host only (no device work): the cull rectangle callers hand to rt_raycast_primary.  Conservative inclusive pixel rect
+// of the scene box [lo, hi] seen from `camera` (projected corners +- 2 px, clamped to the frame); returns 1 and fills
+// rect, or 0 when there is no usable bound (a corner at or behind the eye plane, singular basis, non-finite data).
+int rt_raycast_screen_bounds(const float *camera, const double *lo, const double *hi, int width, int height, int *rect)
+{
+    if (!camera || !lo || !hi || !rect || width <= 0 || height <= 0) return 0;
+    const double o[3] = {camera[0], camera[1], camera[2]};
+    const double U[3] = {camera[3], camera[4], camera[5]}, V[3] = {camera[6], camera[7], camera[8]}, W[3] = {camera[9], camera[10], camera[11]};
+    const double r0[3] = {V[1] * W[2] - V[2] * W[1], V[2] * W[0] - V[0] * W[2], V[0] * W[1] - V[1] * W[0]};
+    const double r1[3] = {W[1] * U[2] - W[2] * U[1], W[2] * U[0] - W[0] * U[2], W[0] * U[1] - W[1] * U[0]};
+    const double r2[3] = {U[1] * V[2] - U[2] * V[1], U[2] * V[0] - U[0] * V[2], U[0] * V[1] - U[1] * V[0]};
+    const double det = U[0] * r0[0] + U[1] * r0[1] + U[2] * r0[2];
+    if (!(det != 0.0) || !(det - det == 0.0)) return 0;
+    double extent = 0.0;
+    for (int k = 0; k < 3; ++k) extent = hi[k] - lo[k] > extent ? hi[k] - lo[k] : extent;
+    const double c_floor = 1e-6 * (extent > 1e-30 ? extent : 1e-30);
+    double smin = INFINITY, smax = -INFINITY, tmin = INFINITY, tmax = -INFINITY;
+    for (int k = 0; k < 8; ++k) {
+        const double q[3] = {((k & 4) ? hi[0] : lo[0]) - o[0], ((k & 2) ? hi[1] : lo[1]) - o[1], ((k & 1) ? hi[2] : lo[2]) - o[2]};
+        const double c = (r2[0] * q[0] + r2[1] * q[1] + r2[2] * q[2]) / det;
+        if (!(c > c_floor) || !(c - c == 0.0)) return 0;
+        const double s = (r0[0] * q[0] + r0[1] * q[1] + r0[2] * q[2]) / det / c, t = (r1[0] * q[0] + r1[1] * q[1] + r1[2] * q[2]) / det / c;
+        if (!(s - s == 0.0) || !(t - t == 0.0)) return 0;
+        smin = s < smin ? s : smin; smax = s > smax ? s : smax; tmin = t < tmin ? t : tmin; tmax = t > tmax ? t : tmax;
+    }
+    const double big = 1073741824.0; // keeps the int conversion defined for far off-screen boxes
+    auto clampd = [&](double v) { return v < -big ? -big : (v > big ? big : v); };
+    const double px0 = clampd(floor((smin + 1.0) * (width * 0.5) - 0.5) - 2.0), px1 = clampd(ceil((smax + 1.0) * (width * 0.5) - 0.5) + 2.0);
+    const double py0 = clampd(floor((1.0 - tmax) * (height * 0.5) - 0.5) - 2.0), py1 = clampd(ceil((1.0 - tmin) * (height * 0.5) - 0.5) + 2.0);
+    rect[0] = px0 > 0.0 ? (int)px0 : 0; rect[1] = py0 > 0.0 ? (int)py0 : 0;
+    rect[2] = px1 < width - 1 ? (int)px1 : width - 1; rect[3] = py1 < height - 1 ? (int)py1 : height - 1;
+    return 1;
+}
+
 int64_t rt_raycast_view_node_bytes(int64_t n_triangles)
 {
     return (int64_t)sizeof(ViewNode) * (n_triangles > 1 ? n_triangles - 1 : 1);

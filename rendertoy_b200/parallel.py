@@ -8,6 +8,10 @@ collective: finished BGRA8 framebuffer pieces are gathered to rank 0 (NCCL over 
   frame_indices(n_frames, rank, world) animation batches: rank r renders frames k = r (mod world)
   gather_tiles / gather_frames         the collective (grouped isend/irecv, i.e. ncclSend/ncclRecv: NCCL has no
                                        native gather)
+  FrameStore                           the same collective over CUDA IPC peer memory: rank 0's store is every rank's
+                                       render target (fused stores) or the destination of copy-engine pushes
+  cover_rect / SparseFrameCopier       sparse frame movement: a ray-cast frame is the clear colour outside the scene's
+                                       projected bounds, so only that pixel rectangle travels (NVLink push, PCIe read-back)
 """
 from typing import List, Tuple
 
@@ -81,6 +85,59 @@ def gather_frames(local_frames: torch.Tensor, all_frames: torch.Tensor, n_frames
             req.wait()
 
 
+def _empty(r):
+    return r is None or r[2] < r[0] or r[3] < r[1]
+
+
+def cover_rect(prev, cur, width, height, align_px=32):
+    """The inclusive pixel rect (x0, y0, x1, y1) that has to be copied so that a destination frame which currently
+    holds a frame with content rect `prev` (None: still cleared) becomes the frame with content rect `cur`, given
+    that the SOURCE frame is the clear colour everywhere outside `cur`: the union of both (the part of `prev` outside
+    `cur` is overwritten with the source's clear pixels), clipped to the frame, columns widened to multiples of
+    `align_px` pixels (32 px = one 128-byte line) so the copy engine moves whole lines.  None: nothing to move."""
+    if _empty(prev) and _empty(cur):
+        return None
+    if _empty(prev):
+        x0, y0, x1, y1 = cur
+    elif _empty(cur):
+        x0, y0, x1, y1 = prev
+    else:
+        x0, y0, x1, y1 = min(prev[0], cur[0]), min(prev[1], cur[1]), max(prev[2], cur[2]), max(prev[3], cur[3])
+    x0, y0, x1, y1 = max(0, x0), max(0, y0), min(width - 1, x1), min(height - 1, y1)
+    if x1 < x0 or y1 < y0:
+        return None
+    x0 = x0 // align_px * align_px
+    x1 = min(width, (x1 // align_px + 1) * align_px) - 1
+    return x0, y0, x1, y1
+
+
+class SparseFrameCopier:
+    """Moves BGRA8 frames that are clear outside a known content rect (what Raycaster.render returns) into destinations
+    that persist between frames -- a slot of the frame store, a pinned host frame -- copying only cover_rect(previous
+    content of that destination, this frame's content) with one pitched copy-engine transfer (rt_copy_rect).  The
+    destination must start cleared (FrameStore does; torch.zeros(...).pin_memory() for host frames) and every frame
+    that goes into it must go through the same copier."""
+
+    def __init__(self, width, height):
+        from . import _native
+        self._native, self.width, self.height = _native, width, height
+        self._content = {}          # destination key -> content rect of the frame it holds
+        self.bytes_moved = 0
+
+    def copy(self, key, dst_ptr, src_ptr, content, stream):
+        """Enqueue on `stream` (raw cudaStream_t).  key: anything hashable naming the destination frame."""
+        r = cover_rect(self._content.get(key), content, self.width, self.height)
+        self._content[key] = content
+        if r is None:
+            return 0
+        x0, y0, x1, y1 = r
+        off, pitch = 4 * (y0 * self.width + x0), 4 * self.width
+        self._native.call("rt_copy_rect", dst_ptr + off, pitch, src_ptr + off, pitch, 4 * (x1 - x0 + 1), y1 - y0 + 1, stream)
+        n = 4 * (x1 - x0 + 1) * (y1 - y0 + 1)
+        self.bytes_moved += n
+        return n
+
+
 class _RawDeviceMemory:
     """Adapter exposing a raw device address to torch through __cuda_array_interface__."""
 
@@ -133,10 +190,25 @@ class FrameStore:
         self.ok = ok and self._base is not None
         self.memory = torch.as_tensor(_RawDeviceMemory(self._base, nbytes), device="cuda") if self.ok else None
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
+        self._copier = None
+        if self.ok and self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()      # rank dst's zero-fill of the store (rt_peer_alloc) is complete before anybody writes into it
 
     def frame(self, k):
         """uint8 view (frame_bytes,) of frame k."""
         return self.memory[k * self.frame_bytes:(k + 1) * self.frame_bytes]
+
+    def frame_ptr(self, k):
+        return self._base + k * self.frame_bytes
+
+    def push(self, k, src_ptr, content, stream):
+        """Copy-engine push of a locally rendered frame into slot k: only the pixel rect that can differ from what the slot
+        holds travels (see SparseFrameCopier; the store starts cleared).  content: the rect Raycaster.render returned.
+        Do not mix with kernels rendering into the same slot.  Returns the bytes enqueued."""
+        if self._copier is None:
+            self._copier = SparseFrameCopier(self.width, self.height)
+        return self._copier.copy(k, self._base + k * self.frame_bytes, src_ptr, content, stream)
 
     def frames(self):
         """(n_frames, H, W) int32 view -- meaningful on rank `dst` after commit()."""

@@ -19,6 +19,7 @@ What changed and why
   * :421-548 host matrices     restated with the NumPy-1.x casting rules they were written for (the
                                                       reference raises under NumPy 2)
 """
+import ctypes
 import inspect
 import math
 import os
@@ -33,6 +34,7 @@ from .. import _native
 # vector dtypes (pyopencl.cltypes layout: names s0.., titles x y z w; 3-vectors padded to 4)
 # ---------------------------------------------------------------------------------------------------
 
+_C_FLOAT = ctypes.c_float
 _ALIGN = {}  # np.dtype -> OpenCL alignment in bytes
 _CNAME = {}  # np.dtype -> C type name (for the kernel DSL)
 
@@ -107,7 +109,7 @@ def to_array(v):
     """Structured vector value(s) -> plain float32 array (rendering/_core.py:169-181)."""
     shape = v.shape
     if shape == ():
-        v = np.expand_dims(v, 0)
+        v = v.reshape(1)        # a 0-d structured value cannot be viewed as its scalars
     if v.dtype == float2:
         return v.view(np.float32).reshape(*shape, 2)
     if v.dtype == float3:
@@ -703,9 +705,15 @@ def scale(*args):
                          0.0, 0.0, 0.0, 1.0)
 
 
-def rotate(angle, axis):
-    """Axis-angle rotation.  NumPy-1 semantics of the reference expression: products of two float32 axis
-    components stay float32, everything touching cos/sin is float64, one rounding to float32 at the end."""
+def _r32(x):
+    """Round a Python float to float32 and back.  IEEE double has 53 >= 2*24 + 2 mantissa bits, so one double operation on
+    float32 operands followed by this rounding IS the float32 operation (double rounding is innocuous for + - * / sqrt):
+    the scalar paths below reproduce NumPy's float32 array arithmetic bit for bit without its per-call overhead."""
+    return _C_FLOAT(x).value
+
+
+def _rotate_numpy(angle, axis):
+    """rotate() as first written, on NumPy arrays; kept as the definition the scalar version is tested against."""
     c, s = np.float64(np.cos(angle)), np.float64(np.sin(angle))
     ax = to_array(axis)
     k = 1 - c
@@ -721,6 +729,22 @@ def rotate(angle, axis):
     m[2, 0] += y * s; m[2, 1] -= x * s
     m[3, :] = (0, 0, 0, 1); m[:3, 3] = 0
     return make_float4x4(*m.ravel().tolist())
+
+
+def rotate(angle, axis):
+    """Axis-angle rotation.  NumPy-1 semantics of the reference expression: products of two float32 axis
+    components stay float32, everything touching cos/sin is float64, one rounding to float32 at the end.
+    Scalar arithmetic (see _r32): a tutorial frame calls this once and the array version costs ~25 us."""
+    if not (isinstance(axis, np.ndarray) and axis.dtype == float3 and axis.shape == ()):
+        return _rotate_numpy(angle, axis)
+    c, s = float(np.cos(angle)), float(np.sin(angle))
+    x, y, z, _ = axis.item()
+    k = 1 - c
+    xx, yy, zz, xy, xz, yz = _r32(x * x), _r32(y * y), _r32(z * z), _r32(x * y), _r32(x * z), _r32(y * z)
+    return make_float4x4(xx * k + c, xy * k + z * s, xz * k - y * s, 0.0,
+                         xy * k - z * s, yy * k + c, yz * k + x * s, 0.0,
+                         xz * k + y * s, yz * k - x * s, zz * k + c, 0.0,
+                         0.0, 0.0, 0.0, 1.0)
 
 
 def matmul(a, b):
@@ -764,7 +788,8 @@ def direction(f, t):
     return normalize(make_float3((to_array(t) - to_array(f)).astype(np.float32)))
 
 
-def look_at(camera, target, up_vector):
+def _look_at_numpy(camera, target, up_vector):
+    """look_at() through the public vector helpers; kept as the definition the scalar version is tested against."""
     zaxis = direction(camera, target)
     xaxis = normalize(cross(up_vector, zaxis))
     yaxis = cross(zaxis, xaxis)
@@ -772,6 +797,41 @@ def look_at(camera, target, up_vector):
     rows = [[c[k] for c in cols] + [0] for k in "xyz"]
     rows.append([-dot(c, camera) for c in cols] + [1])
     return make_float4x4(*[e for r in rows for e in r])
+
+
+def _normalize3(x, y, z):
+    """normalize() of a float3 on scalars: float32 dot, float64 sqrt rounded to float32, float32 divisions."""
+    l = _r32(math.sqrt(_r32(_r32(_r32(x * x) + _r32(y * y)) + _r32(z * z))))
+    if l == 0.0:
+        return None
+    return _r32(x / l), _r32(y / l), _r32(z / l)
+
+
+def _cross3(a, b):
+    return (_r32(_r32(a[1] * b[2]) - _r32(a[2] * b[1])), _r32(_r32(a[2] * b[0]) - _r32(a[0] * b[2])),
+            _r32(_r32(a[0] * b[1]) - _r32(a[1] * b[0])))
+
+
+def _dot3(a, b):
+    return _r32(_r32(_r32(a[0] * b[0]) + _r32(a[1] * b[1])) + _r32(a[2] * b[2]))
+
+
+def look_at(camera, target, up_vector):
+    """View matrix with the camera axes as columns (rendering/_core.py:528-538).  Scalar float32 arithmetic (see _r32),
+    bit-identical to the helper-based formulation in _look_at_numpy, which costs ~60 us per call."""
+    ok = all(isinstance(v, np.ndarray) and v.dtype == float3 and v.shape == () for v in (camera, target, up_vector))
+    if not ok:
+        return _look_at_numpy(camera, target, up_vector)
+    cam, tgt, up = camera.item()[:3], target.item()[:3], up_vector.item()[:3]
+    zaxis = _normalize3(_r32(tgt[0] - cam[0]), _r32(tgt[1] - cam[1]), _r32(tgt[2] - cam[2]))
+    xaxis = _normalize3(*_cross3(up, zaxis)) if zaxis is not None else None
+    if xaxis is None:       # degenerate input: let NumPy produce its inf/nan pattern (and warnings) as before
+        return _look_at_numpy(camera, target, up_vector)
+    yaxis = _cross3(zaxis, xaxis)
+    return make_float4x4(xaxis[0], yaxis[0], zaxis[0], 0,
+                         xaxis[1], yaxis[1], zaxis[1], 0,
+                         xaxis[2], yaxis[2], zaxis[2], 0,
+                         -_dot3(xaxis, cam), -_dot3(yaxis, cam), -_dot3(zaxis, cam), 1)
 
 
 def perspective(fov=3.141593 / 4, aspect_ratio=1.0, znear=.01, zfar=100.0):

@@ -12,6 +12,8 @@ oracle/raycast_oracle.c (float32 Moller-Trumbore, closest hit by (t bits, triang
   render(...)    the fused hot path: primary rays of a camera for a pixel rect -> hits and/or shaded BGRA8
                  written straight into a render target (Lambert of lesson08:42 or texture of lesson09:90-95)
 """
+import ctypes
+import math
 import typing
 
 import numpy as np
@@ -24,6 +26,8 @@ from ._modeling import Mesh
 
 # render(): above this size the per-frame projection of the BVH (reads 64 B, writes 48 B per node) costs more than
 # the cheaper node test saves
+_CAM12 = ctypes.c_float * 12
+_MAT16 = ctypes.c_float * 16
 VIEW_NODES_MAX_TRIANGLES = 1 << 18
 # default builder: clustering pays where the traversal is the bound (the screen-space packet path)
 PLOC_MAX_TRIANGLES = 1 << 18
@@ -61,24 +65,29 @@ class RayHit:
     v: np.float32
 
 
+def _mat16(x):
+    """float4x4 value / (4, 4) array / 16 numbers -> (c_float * 16), row-major."""
+    x = np.asarray(x)
+    if x.dtype != _core.float4x4:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+    assert x.nbytes == 64, "expected a 4x4 matrix"
+    a = _MAT16()
+    ctypes.memmove(a, x.ctypes.data, 64)
+    return a
+
+
 def camera_frame(view, proj, world=None):
     """{origin, U, V, W} (12 float32, model space) of the reference camera convention (rendering/_core.py:
     528-548): a pixel centre with NDC coordinates (sx, sy) looks along U*sx + V*sy + W.
-    view/proj/world: float4x4 values (or 4x4 arrays), row-vector convention.  Computed in float64, rounded once."""
-    def m(x):
-        x = np.asarray(x)
-        if x.dtype == _core.float4x4:
-            x = _core.to_array(x)
-        return np.asarray(x, dtype=np.float64).reshape(4, 4)
-    view, proj = m(view), m(proj)
-    r = view[0:3, 0:3]                                  # columns: xaxis, yaxis, zaxis
-    eye = -(view[3, 0:3] @ np.linalg.inv(r))
-    u, v, w = r[:, 0] / proj[0, 0], r[:, 1] / proj[1, 1], r[:, 2]
-    if world is not None:
-        winv = np.linalg.inv(m(world))
-        eye = (np.append(eye, 1.0) @ winv)[:3]
-        u, v, w = ((np.append(x, 0.0) @ winv)[:3] for x in (u, v, w))
-    return np.concatenate([eye, u, v, w]).astype(np.float32)
+    view/proj/world: float4x4 values (or 4x4 arrays), row-vector convention.  Computed in float64, rounded once
+    (rt_camera_frame, host arithmetic in the native library: this runs once per frame and the same thing through numpy --
+    two LAPACK inversions of tiny matrices -- costs more host time than the GPU needs for the 4K frame)."""
+    out = np.empty(12, np.float32)
+    ok = _native.lib().rt_camera_frame(_mat16(view), _mat16(proj), None if world is None else _mat16(world),
+                                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    if not ok:
+        raise np.linalg.LinAlgError("camera_frame: singular view rotation or world matrix (or non-finite entries)")
+    return out
 
 
 class Raycaster:
@@ -128,6 +137,7 @@ class Raycaster:
         self.scene_lo = xyz.amin(0).double().cpu().numpy()
         self.scene_hi = xyz.amax(0).double().cpu().numpy()
         self.scene_extent = float((self.scene_hi - self.scene_lo).max())
+        self._lo3, self._hi3 = (ctypes.c_double * 3)(*self.scene_lo.tolist()), (ctypes.c_double * 3)(*self.scene_hi.tolist())
         dev = self.pos4.device
         L = _native.lib()
         n = self.n_triangles
@@ -177,21 +187,14 @@ class Raycaster:
 
     def screen_bounds(self, camera, W, H):
         """Conservative inclusive pixel rect [x0, y0, x1, y1] containing every pixel whose primary ray can hit the
-        scene's bounding box (projected corners +- 2 px), or None when the box reaches behind the eye."""
-        cam = np.asarray(camera, np.float64).reshape(4, 3)
-        o, basis = cam[0], cam[1:4].T                      # columns U, V, W: p - o = a*U + b*V + c*W
-        lo, hi = self.scene_lo, self.scene_hi
-        corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
-        try:
-            abc = np.linalg.solve(basis, (corners - o).T)
-        except np.linalg.LinAlgError:
+        scene's bounding box (projected corners +- 2 px), or None when the box reaches behind the eye.
+        Host arithmetic only, but native (rt_raycast_screen_bounds): it runs once per frame, and eight corners through
+        numpy cost ~50 us of a ~120 us frame."""
+        cam = camera if isinstance(camera, _CAM12) else _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12)
+        rect = (ctypes.c_int * 4)()
+        if not _native.lib().rt_raycast_screen_bounds(cam, self._lo3, self._hi3, W, H, rect):
             return None
-        if not np.all(np.isfinite(abc)) or abc[2].min() <= 1e-6 * max(self.scene_extent, 1e-30):
-            return None
-        px = (abc[0] / abc[2] + 1.0) * (W * 0.5) - 0.5
-        py = (1.0 - abc[1] / abc[2]) * (H * 0.5) - 0.5
-        return (int(max(0, np.floor(px.min()) - 2)), int(max(0, np.floor(py.min()) - 2)),
-                int(min(W - 1, np.ceil(px.max()) + 2)), int(min(H - 1, np.ceil(py.max()) + 2)))
+        return rect[0], rect[1], rect[2], rect[3]
 
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
@@ -202,7 +205,9 @@ class Raycaster:
         hits are wanted (then frame_size=(W, H) is required).  stats: optional int64[3] tensor; the instrumented kernel
         adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds.
         view_nodes: project the BVH into this camera's screen space first and traverse that (default: yes up to
-        VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself)."""
+        VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself).
+        Returns the inclusive frame-pixel rect (x0, y0, x1, y1) outside of which everything this call wrote is the clear
+        colour / a miss (the cull rect clipped to `rect`; x1 < x0 when nothing can be hit) -- what a sparse gather has to move."""
         if render_target is not None:
             W, H = render_target.width, render_target.height
         else:
@@ -219,14 +224,15 @@ class Raycaster:
             if (x0, y0, w, h) == (0, 0, W, H):
                 render_target.take_pending_clear()
             bgra_ptr = render_target.ptr + 4 * (y0 * W + x0)
-        cam32 = np.ascontiguousarray(camera, np.float32).reshape(12)
+        cam_c = _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12)
         rect_c = None
+        content = (x0, y0, x0 + w - 1, y0 + h - 1)
         if cull:
-            r = self.screen_bounds(cam32, W, H)
-            if r is not None:
-                import ctypes
-                rect_c = (ctypes.c_int * 4)(*r)
-        fast_slab = int(float(np.abs(cam32[0:3]).max()) <= 16.0 * self.scene_extent)
+            r = (ctypes.c_int * 4)()
+            if _native.lib().rt_raycast_screen_bounds(cam_c, self._lo3, self._hi3, W, H, r):
+                rect_c = r
+                content = (max(x0, r[0]), max(y0, r[1]), min(x0 + w - 1, r[2]), min(y0 + h - 1, r[3]))
+        fast_slab = int(max(abs(cam_c[0]), abs(cam_c[1]), abs(cam_c[2])) <= 16.0 * self.scene_extent)
         if view_nodes is None:
             view_nodes = self.n_triangles <= VIEW_NODES_MAX_TRIANGLES
         vn_ptr = None
@@ -238,8 +244,9 @@ class Raycaster:
             vn_ptr = self._view_nodes[stream].data_ptr()
         _native.call("rt_raycast_primary", self.nodes.data_ptr(), self.tris.data_ptr(), self.n_triangles, self.pos4.data_ptr(),
                      self.nrm4.data_ptr(), self._idx_ptr(),
-                     _native.float_array_from_bytes(cam32.view(np.uint8), 12),
+                     cam_c,
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
                      None if stats is None else stats.data_ptr(), rect_c, fast_slab, vn_ptr, stream_ptr())
         if render_target is not None:
             render_target._buffer.device_written()
+        return content

@@ -206,3 +206,65 @@ def test_kernels_fail_loudly_without_cuda(ren):
     vb = ren.create_buffer(3, ren.MeshVertex)
     with pytest.raises(Exception):
         raster.draw_triangles(vb, None)       # no CPU fallback: the native call refuses
+
+
+def test_scalar_rotate_and_look_at_equal_the_numpy_formulations(ren):
+    """rotate()/look_at() run on Python scalars with explicit float32 roundings (a frame calls them once each and the
+    array versions cost ~90 us together); they must reproduce the NumPy formulations bit for bit, degenerate input included."""
+    import warnings
+    from rendering import _core
+    rng = np.random.default_rng(11)
+
+    def f3(scale=1.0):
+        return ren.make_float3(*(rng.standard_normal(3) * scale).astype(np.float32).tolist())
+
+    for k in range(1500):
+        axis = f3(10.0 ** rng.integers(-6, 6))
+        angle = float(rng.uniform(-10, 10)) if k % 3 else np.float32(rng.uniform(-10, 10))
+        assert np.asarray(_core.rotate(angle, axis)).tobytes() == np.asarray(_core._rotate_numpy(angle, axis)).tobytes()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(1500):
+            s = 10.0 ** rng.integers(-3, 4)
+            cam, tgt, up = f3(s), f3(s), f3()
+            if k % 5 == 0:
+                up = ren.make_float3(0, 1, 0)
+            if k % 11 == 0:
+                tgt = ren.make_float3(0, 0, 0)
+            if k % 300 == 0:
+                tgt = cam                                   # zero view direction: NumPy's nan pattern must come through
+            if k % 301 == 0:
+                up = ren.make_float3(*[float(x) for x in (ren.to_array(tgt) - ren.to_array(cam))])   # up parallel to the view direction
+            a, b = _core.look_at(cam, tgt, up), _core._look_at_numpy(cam, tgt, up)
+            assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+
+
+def test_camera_frame_native_matches_float64_numpy(ren):
+    """rt_camera_frame (host arithmetic in the native library) against the float64 NumPy formulation: same frame up to the
+    last float32 bit of components that are not cancellation noise; singular input raises."""
+    from rendering._raycaster import camera_frame
+    from rendertoy_b200 import scenes
+
+    def numpy_frame(view, proj, world):
+        m = lambda x: ren.to_array(np.asarray(x, dtype=ren.float4x4)).astype(np.float64).reshape(4, 4)
+        view, proj = m(view), m(proj)
+        r = view[0:3, 0:3]
+        eye = -(view[3, 0:3] @ np.linalg.inv(r))
+        u, v, w = r[:, 0] / proj[0, 0], r[:, 1] / proj[1, 1], r[:, 2]
+        if world is not None:
+            winv = np.linalg.inv(m(world))
+            eye = (np.append(eye, 1.0) @ winv)[:3]
+            u, v, w = ((np.append(x, 0.0) @ winv)[:3] for x in (u, v, w))
+        return np.concatenate([eye, u, v, w])
+
+    for k in range(200):
+        world, view, proj = scenes.lesson_camera(ren, 6 if k % 2 else 8, 0.0731 * k, 1920, 1080)
+        if k % 4 == 0:      # scaled, translated world: the general inverse
+            world = ren.matmul(ren.scale(1.0 + 0.01 * k, 0.5, 2.0), np.array(ren.translate(0.1, 0.02 * k, -0.3), dtype=ren.float4x4))
+        world = None if k % 7 == 0 else np.array(world, dtype=ren.float4x4)
+        got = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), world)
+        want = numpy_frame(view, proj, world)
+        assert got.dtype == np.float32 and got.shape == (12,)
+        assert np.allclose(got, want, rtol=3e-7, atol=1e-7 * np.abs(want).max())
+    with pytest.raises(np.linalg.LinAlgError):
+        camera_frame(np.zeros((4, 4), np.float32), np.eye(4, dtype=np.float32))

@@ -69,3 +69,94 @@ def test_gather_world_size_2_gloo():
         p.join(100)
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+# ---- sparse frame movement (cover_rect / SparseFrameCopier) -------------------------------------------------------
+
+def _fake_copy_rect(name, dst, dst_pitch, src, src_pitch, width_bytes, rows, stream):
+    """What rt_copy_rect does (cudaMemcpy2DAsync), on host memory."""
+    import ctypes
+    assert name == "rt_copy_rect" and dst_pitch >= width_bytes and src_pitch >= width_bytes
+    for r in range(rows):
+        ctypes.memmove(dst + r * dst_pitch, src + r * src_pitch, width_bytes)
+
+
+def test_cover_rect_cases():
+    W, H = 200, 100
+    assert parallel.cover_rect(None, (5, 1, 4, 9), W, H) is None                 # nothing before, nothing now
+    assert parallel.cover_rect(None, (40, 10, 70, 20), W, H) == (32, 10, 95, 20)  # columns widen to 32-px lines
+    assert parallel.cover_rect((40, 10, 70, 20), (5, 1, 4, 9), W, H) == (32, 10, 95, 20)   # the old content must be cleared
+    assert parallel.cover_rect((0, 0, 10, 10), (150, 50, 199, 99), W, H) == (0, 0, 199, 99)
+    assert parallel.cover_rect(None, (190, 0, 500, 500), W, H) == (160, 0, 199, 99)  # clipped; last line partial
+    assert parallel.cover_rect(None, (-20, -5, 3, 3), W, H) == (0, 0, 31, 3)
+
+
+def test_sparse_copier_keeps_destinations_exact(monkeypatch):
+    """Random frames that are clear outside a random content rect, cycled through two persistent destinations:
+    after every copy the destination must equal the source frame everywhere, with far fewer bytes moved."""
+    from rendertoy_b200 import _native
+    monkeypatch.setattr(_native, "call", _fake_copy_rect)
+    rng = np.random.default_rng(7)
+    W, H = 333, 97
+    copier = parallel.SparseFrameCopier(W, H)
+    dests = [np.zeros((H, W), np.uint32) for _ in range(2)]
+    moved = 0
+    for it in range(200):
+        src = np.zeros((H, W), np.uint32)
+        kind = it % 10
+        if kind == 0:
+            content = (5, 5, 4, 4)                                               # empty: nothing can be hit
+        elif kind == 1:
+            content = (0, 0, W - 1, H - 1)                                       # no bound known: the whole frame
+        else:
+            x0, x1 = sorted(rng.integers(0, W, 2)); y0, y1 = sorted(rng.integers(0, H, 2))
+            content = (int(x0), int(y0), int(x1), int(y1))
+        if content[2] >= content[0]:
+            x0, y0, x1, y1 = content
+            src[y0:y1 + 1, x0:x1 + 1] = rng.integers(0, 2 ** 32, (y1 - y0 + 1, x1 - x0 + 1), dtype=np.uint32)
+        d = dests[it % 2]
+        moved += copier.copy(it % 2, d.ctypes.data, src.ctypes.data, content, None)
+        assert np.array_equal(d, src), f"iteration {it}: destination differs from the frame"
+    assert moved == copier.bytes_moved and moved < 0.8 * 200 * W * H * 4
+
+
+def test_screen_bounds_native_matches_numpy(ren):
+    """rt_raycast_screen_bounds (host-only C) against the numpy formulation it replaced, lesson cameras + degenerate ones."""
+    import ctypes
+    from rendering._raycaster import Raycaster, camera_frame
+    from rendertoy_b200 import scenes
+    rc = Raycaster.__new__(Raycaster)
+    rc.scene_lo, rc.scene_hi = np.array([-0.5, -0.31, -0.22]), np.array([0.5, 0.27, 0.24])
+    rc.scene_extent = 1.0
+    rc._lo3, rc._hi3 = (ctypes.c_double * 3)(*rc.scene_lo), (ctypes.c_double * 3)(*rc.scene_hi)
+
+    def numpy_bounds(camera, W, H):
+        cam = np.asarray(camera, np.float64).reshape(4, 3)
+        o, basis = cam[0], cam[1:4].T
+        lo, hi = rc.scene_lo, rc.scene_hi
+        corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+        try:
+            abc = np.linalg.solve(basis, (corners - o).T)
+        except np.linalg.LinAlgError:
+            return None
+        if not np.all(np.isfinite(abc)) or abc[2].min() <= 1e-6:
+            return None
+        px = (abc[0] / abc[2] + 1.0) * (W * 0.5) - 0.5
+        py = (1.0 - abc[1] / abc[2]) * (H * 0.5) - 0.5
+        return (int(max(0, np.floor(px.min()) - 2)), int(max(0, np.floor(py.min()) - 2)),
+                int(min(W - 1, np.ceil(px.max()) + 2)), int(min(H - 1, np.ceil(py.max()) + 2)))
+
+    for k in range(64):
+        for lesson, (W, H) in ((6, (3840, 2160)), (8, (1920, 1080)), (6, (333, 211))):
+            world, view, proj = scenes.lesson_camera(ren, lesson, 0.37 * k, W, H)
+            cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+            assert rc.screen_bounds(cam, W, H) == numpy_bounds(cam, W, H)
+    inside = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)           # eye inside the box
+    assert rc.screen_bounds(inside, 640, 480) is None
+    singular = np.array([0, 0, 3, 1, 0, 0, 1, 0, 0, 0, 0, -1], np.float32)        # U == V
+    assert rc.screen_bounds(singular, 640, 480) is None
+    nan = np.array([np.nan, 0, 3, 1, 0, 0, 0, 1, 0, 0, 0, -1], np.float32)
+    assert rc.screen_bounds(nan, 640, 480) is None
+    far = np.array([1e6, 0, 3, 1, 0, 0, 0, 1, 0, 0, 0, -1], np.float32)           # scene far off to the side: clamped, maybe empty
+    r = rc.screen_bounds(far, 640, 480)
+    assert r is None or (0 <= r[0] and r[2] <= 639 and 0 <= r[1] and r[3] <= 479)

@@ -331,3 +331,55 @@ def test_ploc_builder_trees_and_hits(ren, oracle):
         ref = oracle.raycast_brute(np.ascontiguousarray(rows), oracle.primary_rays(cam, w, h))
         _check(a.view(np.float32), ref, label)
         print(f"{label}: n={rows.shape[0] // 3} heights ploc {hp} lbvh {hl}, hit pixels {int((a[:, 1] != 0xFFFFFFFF).sum())}")
+
+
+def test_render_content_rect_holds_every_hit(ren):
+    """render() returns the rect outside of which the frame is the clear colour: the contract of the sparse gather."""
+    from rendering._raycaster import Raycaster
+    rows = scenes.dragon(5_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    for lesson, w, h, t in [(6, 640, 360, 0.3), (8, 333, 211, 2.1), (6, 1920, 1080, 4.0), (8, 96, 64, 5.5)]:
+        cam = _camera(ren, lesson, t, w, h)
+        target = ren.create_image2d(w, h, ren._core.RGBA)
+        target.buffer.tensor().fill_(0x5A)                           # stale pixels everywhere
+        x0, y0, x1, y1 = rc.render(target, cam)
+        img = target.get().view(np.uint32).reshape(h, w)
+        assert (img != 0).any()
+        outside = np.ones((h, w), bool)
+        outside[y0:y1 + 1, x0:x1 + 1] = False
+        assert not img[outside].any(), "non-clear pixel outside the returned content rect"
+        sub = rc.render(target, cam, rect=(8, 4, w - 16, h - 8))     # partial rect: content is clipped to it
+        assert sub[0] >= 8 and sub[1] >= 4 and sub[2] <= w - 9 and sub[3] <= h - 5
+    # camera inside the scene: no bound, the content rect is the whole frame
+    cam = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+    target = ren.create_image2d(64, 48, ren._core.RGBA)
+    assert rc.render(target, cam) == (0, 0, 63, 47)
+
+
+def test_frame_store_sparse_push(ren):
+    """FrameStore.push (rt_copy_rect): an orbit of locally rendered frames cycling through two slots of a cleared store;
+    after every push the slot equals the frame bit for bit although only the cover rect travelled."""
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200 import parallel
+    w, h = 1280, 720
+    rows = scenes.dragon(20_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    store = parallel.FrameStore(2, w, h)
+    assert store.ok
+    try:
+        assert not store.frames().any(), "the store must start cleared"
+        local = ren.create_image2d(w, h, ren._core.RGBA)
+        side = torch.cuda.Stream()
+        moved = 0
+        for k in range(12):
+            cam = _camera(ren, 6 if k % 3 else 8, 0.45 * k, w, h)
+            content = rc.render(local, cam)
+            side.wait_stream(torch.cuda.current_stream())
+            moved += store.push(k % 2, local.ptr, content, side.cuda_stream)
+            torch.cuda.current_stream().wait_stream(side)
+            frame = local.buffer.tensor().view(torch.int32).view(h, w)
+            assert torch.equal(store.frames()[k % 2], frame), f"slot differs from frame {k}"
+            assert frame.any()
+        assert 0 < moved < 0.7 * 12 * w * h * 4
+    finally:
+        store.close()

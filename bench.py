@@ -627,6 +627,11 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (rendertoy_b200 has no CPU path); use --impl reference for the CPU oracle")
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there while the benchmark runs (NCCL's version
+    # banner, for one) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist_setup(args.gpus)
     ray, rows = bench_raycast(args, rank, world)
     ras = bench_raster(args, rank, world, rows)
@@ -650,7 +655,8 @@ def main():
             for k in ("n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "clocks"):
                 primary.setdefault(k, ray.get(k))
         primary["secondary"] = secondary
-        print(json.dumps(primary))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(primary) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -539,40 +539,45 @@ def clear(b, value=np.float32(0)):
         b.buffer._st.write(0, np.tile(px, b.width * b.height))
 
 
+class _Mapped:
+    """The context manager mapped() returns (a module-level class: building one per call costs ~7 us of every frame)."""
+    __slots__ = ("b", "host", "raw", "direct")
+
+    def __init__(self, b):
+        self.b, self.host, self.raw, self.direct = b, None, None, False
+
+    def __enter__(self):
+        b = self.b
+        self.direct = False
+        if isinstance(b, Image):
+            a = b.buffer.get()
+            self.host = a[..., 0] if b.components == 1 else a
+            self.raw = a
+        elif isinstance(b, DeviceBuffer) and b._st.host is not None and b._st.host_valid:
+            # small buffers (shader globals, descriptors): hand out the host shadow itself, no copies
+            self.direct = True
+            self.host = b._st.host[b.offset:b.offset + b.nbytes].view(b.dtype).reshape(b.shape)
+        else:
+            self.host = b.get()
+        return self.host
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        b = self.b
+        if isinstance(b, Image):
+            b.buffer.set(self.raw)
+        elif self.direct:
+            b._st.dev_valid = False
+            b._st.version += 1
+        else:
+            b.set(self.host)
+        return False
+
+
 def mapped(b: typing.Union[DeviceBuffer, Image, DepthView]):
     """Context manager giving a writable numpy view of a buffer/image; changes are copied back on exit
     (rendering/_core.py:391-418).  Shapes follow the reference: images map to (H, W, C) (C dropped when 1),
     arrays to their own shape, 0-d structs to a 0-d structured array."""
-
-    class _ctx:
-        def __init__(self):
-            self.host = None
-
-        def __enter__(self):
-            self.direct = False
-            if isinstance(b, Image):
-                a = b.buffer.get()
-                self.host = a[..., 0] if b.components == 1 else a
-                self.raw = a
-            elif isinstance(b, DeviceBuffer) and b._st.host is not None and b._st.host_valid:
-                # small buffers (shader globals, descriptors): hand out the host shadow itself, no copies
-                self.direct = True
-                self.host = b._st.host[b.offset:b.offset + b.nbytes].view(b.dtype).reshape(b.shape)
-            else:
-                self.host = b.get()
-            return self.host
-
-        def __exit__(self, exc_type, exc_val, exc_tb):
-            if isinstance(b, Image):
-                b.buffer.set(self.raw)
-            elif self.direct:
-                b._st.dev_valid = False
-                b._st.version += 1
-            else:
-                b.set(self.host)
-            return False
-
-    return _ctx()
+    return _Mapped(b)
 
 
 # ---------------------------------------------------------------------------------------------------

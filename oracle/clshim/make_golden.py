@@ -238,6 +238,137 @@ def run_custom(out_dir):
                         ambient=np.float32(0.25), texture_rgb=tex, depth=depth, bgra=bgra, shaders=CUSTOM_SHADERS)
 
 
+SCENE_SOURCE = '''
+@ren.kernel_struct
+class SceneTransforms:
+    World: ren.float4x4
+    View: ren.float4x4
+    Proj: ren.float4x4
+
+@ren.kernel_struct
+class SceneMaterial:
+    DiffuseMap: ren.Texture2D
+
+@ren.kernel_struct
+class SceneVertexOut:
+    proj: ren.float4
+    L: ren.float3
+    C: ren.float2
+
+@ren.kernel_function
+def scene_vs(vertex: ren.MeshVertex, info: SceneTransforms) -> SceneVertexOut:
+    """
+    float d = 0.25f + max(0.0f, dot(vertex.N, normalize((float3)(1.0f, 2.0f, 1.5f))));
+    float4 H = (float4)(vertex.P.x, vertex.P.y, vertex.P.z, 1.0f);
+    H = mul(H, info.World);
+    H = mul(H, info.View);
+    H = mul(H, info.Proj);
+    SceneVertexOut o;
+    o.proj = H;
+    o.L = (float3)(d, d * 0.9f, d * 0.8f);
+    o.C = vertex.C;
+    return o;
+    """
+
+@ren.kernel_function
+def scene_fs(fragment: SceneVertexOut, info: SceneMaterial) -> ren.float4:
+    """
+    float3 texel = sample2D(info.DiffuseMap, fragment.C).xyz;
+    return (float4)(texel * fragment.L, 1.0f);
+    """
+
+@ren.kernel_main
+def lathe(vertices: [ren.MeshVertex], radius_scale: np.float32):
+    """
+    float2 uv = vertices[thread_id].C;
+    float knots[] = {0.0f, 0.2f, 0.45f, 0.7f, 1.0f};
+    float radii[] = {0.02f, 0.30f, 0.12f, 0.22f, 0.05f};
+    float3 p = (float3)(0, 0, 0);
+    for (int i = 1; i < 5; i++) {
+        if (uv.x <= knots[i]) {
+            float a = (uv.x - knots[i - 1]) / (knots[i] - knots[i - 1]);
+            p = (float3)((radii[i - 1] * (1 - a) + radii[i] * a) * radius_scale, uv.x - 0.5f, 0);
+            break;
+        }
+    }
+    float4x4 rot = rotation(uv.y * 6.2831853f, (float3)(0, 1, 0));
+    float4 h = (float4)(p.x, p.y, p.z, 1.0f);
+    h = mul(h, rot);
+    float3 n = normalize((float3)(1.0f, 0.5f, 0.0f));
+    float4 nh = (float4)(n.x, n.y, n.z, 0.0f);
+    nh = mul(nh, rot);
+    vertices[thread_id].N = nh.xyz;
+    vertices[thread_id].P = h.xyz;
+    """
+
+@ren.kernel_main
+def place(vertices: [ren.MeshVertex], m: ren.float4x4):
+    """
+    float3 P = vertices[thread_id].P;
+    float4 H = (float4)(P.x, P.y, P.z, 1.0f);
+    H = mul(H, m);
+    H.xyz /= H.w;
+    vertices[thread_id].P = H.xyz;
+    """
+'''
+
+
+def run_scene(out_dir):
+    """A small multi-mesh scene in the style of Class2022/*/scene.py, through the reference itself: `manifold` grids bent by
+    @kernel_main kernels (local arrays, for/break, rotation(), a matrix passed by value), then several indexed draws with
+    different textures and a draw_points overlay composing on one depth/colour target.  The golden keeps the vertex data
+    the reference's kernels produced (sin/cos of the host libm differ from CUDA's by ulps) and the final targets."""
+    ns = {"ren": ren, "np": np}
+    exec(SCENE_SOURCE, ns)
+    w, h = 200, 150
+    rng = np.random.default_rng(21)
+    specs = [(24, 20, 1.0, hm.translate(-0.25, 0.0, 0.0)), (16, 18, 0.7, hm.matmul(hm.scale(0.8), hm.translate(0.3, 0.05, 0.1))),
+             (10, 10, 0.0, hm.matmul(hm.matmul(hm.translate(-0.5, -0.5, 0.0), hm.rotate(np.pi / 2, (1, 0, 0))), hm.translate(0.0, -0.5, 0.0)))]
+    meshes, grids, lathed, placed, index_data, textures = [], [], [], [], [], []
+    for slices, stacks, rscale, M in specs:
+        mesh = ren.manifold(slices, stacks)
+        grids.append(np.array(mesh.vertices.get()).view(np.float32).reshape(-1, 20).copy())
+        if rscale > 0:
+            ns["lathe"][mesh.vertices.shape](mesh.vertices, np.float32(rscale))
+        lathed.append(np.array(mesh.vertices.get()).view(np.float32).reshape(-1, 20).copy())
+        ns["place"][mesh.vertices.shape](mesh.vertices, np.ascontiguousarray(M, np.float32))
+        placed.append(np.array(mesh.vertices.get()).view(np.float32).reshape(-1, 20).copy())
+        index_data.append(np.array(mesh.indices.get()).astype(np.int32).copy())
+        meshes.append(mesh)
+        textures.append(rng.integers(0, 256, size=(11 + 2 * len(textures), 9 + len(textures), 3), dtype=np.uint8))
+    target = ren.create_image2d(w, h, ren._core.RGBA)
+    g, fg = ren.create_struct(ns["SceneTransforms"]), ren.create_struct(ns["SceneMaterial"])
+    raster = ren.Raster(target, ns["scene_vs"], g, ns["scene_fs"], fg)
+    W, V, P = hm.scale(0.9), hm.look_at((0.1, 0.5, 1.3), (0, 0, 0), (0, 1, 0)), hm.perspective(aspect_ratio=w / h)
+    set_globals(g, W, V, P)
+    descs = []
+    for tex in textures:
+        mem, desc = ren.create_texture2D(tex.shape[1], tex.shape[0])
+        with ren.mapped(mem) as m:
+            m = m.view(np.float32).ravel().reshape(tex.shape[0], tex.shape[1], 4)
+            m[:, :, 0:3] = tex / 255.0
+            m[:, :, 3] = 1.0
+        descs.append(desc)
+    ren.clear(raster.get_render_target())
+    ren.clear(raster.get_depth_buffer(), 1.0)
+    for mesh, desc in zip(meshes, descs):
+        with ren.mapped(fg) as m:
+            m["DiffuseMap"] = desc.get()
+        raster.draw_triangles(mesh.vertices, mesh.indices)
+    depth_tris, bgra_tris = read_targets(raster, target)
+    raster.draw_points(meshes[0].vertices)          # last material still bound
+    depth, bgra = read_targets(raster, target)
+    print(f"scene2022: triangles cover {int((depth_tris != 0x3F800000).sum())} of {w * h}, points changed {int((bgra != bgra_tris).any(axis=-1).sum())} pixels")
+    np.savez_compressed(os.path.join(out_dir, "scene2022.npz"), source=SCENE_SOURCE, width=w, height=h,
+                        globals=np.concatenate([W.ravel(), V.ravel(), P.ravel()]).astype(np.float32),
+                        specs=np.array([(a, b, c) for a, b, c, _ in specs], np.float32), place=np.stack([np.asarray(M, np.float32) for *_, M in specs]),
+                        depth_tris=depth_tris, bgra_tris=bgra_tris, depth=depth, bgra=bgra,
+                        **{f"grid{i}": x for i, x in enumerate(grids)}, **{f"lathed{i}": x for i, x in enumerate(lathed)},
+                        **{f"placed{i}": x for i, x in enumerate(placed)}, **{f"indices{i}": x for i, x in enumerate(index_data)},
+                        **{f"texture{i}": x for i, x in enumerate(textures)})
+    return 0, 0
+
+
 def cases():
     rng = np.random.default_rng(7)
     tex = rng.integers(0, 256, size=(17, 23, 3), dtype=np.uint8)
@@ -280,10 +411,13 @@ def main():
         if sys.argv[2] == "custom_shaders":
             run_custom(out_dir)
             return 0
+        if sys.argv[2] == "scene2022":
+            run_scene(out_dir)
+            return 0
         r = run_case(sys.argv[2], out_dir=out_dir, **cases()[sys.argv[2]])
         return 0 if r is None or (r[0] == 0 and r[1] == 0) else 1
     import subprocess
-    bad = [n for n in list(cases()) + ["dsl_lesson06", "custom_shaders"] if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
+    bad = [n for n in list(cases()) + ["dsl_lesson06", "custom_shaders", "scene2022"] if subprocess.call([sys.executable, os.path.abspath(__file__), "--case", n], cwd="/tmp") != 0]
     print("ORACLE PINNED: every depth word and every non-tie colour matches the reference run" if not bad else f"MISMATCH in {bad}")
     return 0 if not bad else 1
 

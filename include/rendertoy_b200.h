@@ -169,6 +169,20 @@ int rt_dsl_compile(const char *cuda_source, uint64_t *out_module, char *log, int
 int rt_dsl_launch(uint64_t module, const char *kernel, int64_t n_threads, void **args, void *stream);
 int rt_dsl_unload(uint64_t module);
 
+/* ---- OBJ loading  (rendering/_loaders.py:7-33: pywavefront.Wavefront(path, collect_faces=True), then per mesh the first
+ * material's interleaved, face-corner-expanded vertices) -- host code, no device work -----------------------------------
+ * rt_obj_load parses the file (v / vn / vt / o / usemtl / f with v, v/t, v//n, v/t/n corners, 1-based or negative indices,
+ * polygons fan-triangulated) and returns a handle; meshes are those that own at least one material, in file order.
+ * rt_obj_mesh_info: soup vertex count (3 per triangle), triangle count and the vertex format (bit 0: T2F, bit 1: N3F; V3F
+ * always) of mesh `mesh`.  rt_obj_mesh_rows scatters the soup into caller memory, `row_floats` floats per vertex (20 for
+ * MeshVertex): P at [0..2], N at [4..6] when the format has normals, UV at [8..9] when it has texture coordinates; other
+ * floats are left untouched.  Positions are as in the file: load_obj's normalisation (_loaders.py:34-38) is the caller's. */
+int rt_obj_load(const char *path, uint64_t *out_handle);
+int rt_obj_mesh_count(uint64_t handle);
+int rt_obj_mesh_info(uint64_t handle, int mesh, int64_t *n_vertices, int64_t *n_faces, int *format);
+int rt_obj_mesh_rows(uint64_t handle, int mesh, float *rows, int64_t row_floats);
+int rt_obj_free(uint64_t handle);
+
 /* ---- multi-GPU frame store  (no reference counterpart: rendering/_core.py:10-11 is single-device) -------
  * Rank 0 allocates the store (cudaMalloc, IPC-exportable) and exports a 64-byte handle; the other ranks of the
  * node open it and pass addresses inside it as `d_bgra` to rt_raycast_primary / rt_raster_draw_triangles /

@@ -41,6 +41,11 @@ SIGNATURES = {
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),
     "rt_dsl_launch": (C.c_int, [_U64, C.c_char_p, _I64, C.POINTER(_VP), _VP]),
     "rt_dsl_unload": (C.c_int, [_U64]),
+    "rt_obj_load": (C.c_int, [C.c_char_p, C.POINTER(_U64)]),
+    "rt_obj_mesh_count": (C.c_int, [_U64]),
+    "rt_obj_mesh_info": (C.c_int, [_U64, _I32, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int)]),
+    "rt_obj_mesh_rows": (C.c_int, [_U64, _I32, _FP, _I64]),
+    "rt_obj_free": (C.c_int, [_U64]),
     "rt_peer_alloc": (C.c_int, [_I64, C.POINTER(_VP)]),
     "rt_peer_free": (C.c_int, [_VP]),
     "rt_peer_export": (C.c_int, [_VP, _VP]),

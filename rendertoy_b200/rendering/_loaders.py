@@ -6,9 +6,15 @@ list (triangle soup in file order; polygons fan-triangulated as (v0, v[i-1], v[i
 V3F / N3F_V3F / T2F_V3F / T2F_N3F_V3F.  pywavefront's version is unpinned by the reference, so this behaviour is
 anchored on that call site only ("parity unpinned").
 
+load_obj parses with the native one-pass parser (rt_obj_load in csrc/rt_obj.cu: host code over the mapped file, ~25x the
+line-by-line Python formulation below, which a dragon-class file keeps busy for seconds).  _parse_obj / _load_obj_python stay
+as the readable definition of the rules; tests compare the two on files that exercise every rule.
+
 After the scatter into MeshVertex rows the positions get the reference's scalar min/max normalisation
 (_loaders.py:34-38) in float32:  P = (P - min) / (max - min) - 0.5.
 """
+import os
+
 import numpy as np
 
 from ._core import create_buffer, mapped
@@ -85,9 +91,44 @@ def _parse_obj(path):
             np.asarray(tex, np.float32).reshape(-1, 2), meshes)
 
 
+def _normalise_positions(rows):
+    """The reference's scalar min/max normalisation (_loaders.py:34-38), float32."""
+    v_min = rows[:, 0:3].min()
+    v_max = rows[:, 0:3].max()
+    v_size = v_max - v_min
+    max_dim = v_size.max()
+    rows[:, 0:3] = (rows[:, 0:3] - v_min) / max_dim - v_size * 0.5 / max_dim
+
+
 def load_obj(path):
     """Returns [(Mesh, None), ...] like the reference: soup MeshVertex buffer + an (unfilled, zero) index
     buffer of len(faces)*3 `int` entries (_loaders.py:17 never writes it; tutorials pass index_buffer=None)."""
+    import ctypes
+    from .. import _native
+    L = _native.lib()
+    handle = ctypes.c_uint64(0)
+    if L.rt_obj_load(os.fsencode(path), ctypes.byref(handle)) != 0:
+        raise Exception(f"load_obj({path!r}): {L.rt_last_error().decode(errors='replace')}")
+    objs = []
+    try:
+        for i in range(L.rt_obj_mesh_count(handle)):
+            nv, nf, fmt = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+            _native.call("rt_obj_mesh_info", handle, i, ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(fmt))
+            mesh_vertices = create_buffer(nv.value, MeshVertex)
+            mesh_indices = create_buffer(nf.value * 3, int)
+            with mapped(mesh_vertices) as map:
+                rows = map.view(np.float32).reshape(nv.value, -1)
+                if L.rt_obj_mesh_rows(handle, i, rows.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), rows.shape[1]) != 0:
+                    raise Exception(f"load_obj({path!r}): {L.rt_last_error().decode(errors='replace')}")
+                _normalise_positions(rows)
+            objs.append((Mesh(mesh_vertices, mesh_indices), None))  # mesh + material
+    finally:
+        L.rt_obj_free(handle)
+    return objs
+
+
+def _load_obj_python(path):
+    """load_obj on the Python parser: the definition the native path is tested against."""
     pos, nrm, tex, meshes = _parse_obj(path)
     objs = []
     for m in meshes:
@@ -109,10 +150,6 @@ def load_obj(path):
                     rows[:, 8:10] = tex[c[:, 1]]
                 else:
                     raise Exception(f'Vertex format in obj {mat.vertex_format} is not supported')
-            v_min = rows[:, 0:3].min()
-            v_max = rows[:, 0:3].max()
-            v_size = v_max - v_min
-            max_dim = v_size.max()
-            rows[:, 0:3] = (rows[:, 0:3] - v_min) / max_dim - v_size * 0.5 / max_dim
+            _normalise_positions(rows)
         objs.append((Mesh(mesh_vertices, mesh_indices), None))  # mesh + material
     return objs

@@ -268,3 +268,83 @@ def test_camera_frame_native_matches_float64_numpy(ren):
         assert np.allclose(got, want, rtol=3e-7, atol=1e-7 * np.abs(want).max())
     with pytest.raises(np.linalg.LinAlgError):
         camera_frame(np.zeros((4, 4), np.float32), np.eye(4, dtype=np.float32))
+
+
+_TRICKY_OBJ = """# comment line
+mtllib nothing.mtl
+v 0 0 0
+v 1 0 0 0.5 0.5 0.5
+v 1 1 0
+v 0 1 0
+v 0.5 0.5 1e0
+v -.25 +2.5e-1 1.
+v 12345678901234567890.5 1e-30 0.1234567890123456789
+vn 0 0 1
+vn 0 1 0
+vn 1 0 0
+vt 0 0
+vt 1 0 0
+vt 1 1
+vt 0.25
+f 1 2 3
+usemtl first
+o quad
+f 1/1/1 2/2/1 3/3/2 4/4/3
+f -4//-1 -3//-2 -2//-3
+g ignored group
+s off
+o second
+f 5/1/1 6/2/2 7/3/3 1/4/1 2/1/2
+usemtl other
+f 1 2 3
+o third
+usemtl first
+f 2/2/2 3/3/3 4/4/1
+o empty_one
+\tv 9 9 9
+   # indented comment
+f 8/1/1 1/1/1 2/2/2\r
+"""
+
+
+def _compare_loaders(ren, path):
+    from rendering import _loaders
+    a, b = ren.load_obj(str(path)), _loaders._load_obj_python(str(path))
+    assert len(a) == len(b)
+    for (ma, _), (mb, _) in zip(a, b):
+        ra, rb = ma.vertices.get().view(np.float32).reshape(-1, 20), mb.vertices.get().view(np.float32).reshape(-1, 20)
+        assert ra.shape == rb.shape
+        assert np.array_equal(ra.view(np.uint32), rb.view(np.uint32)), "native OBJ parser differs from the Python formulation"
+        assert ma.indices.shape == mb.indices.shape and ma.indices.dtype == mb.indices.dtype
+    return a
+
+
+def test_native_obj_parser_matches_python_formulation(ren, tmp_path):
+    p = tmp_path / "tricky.obj"
+    p.write_bytes(_TRICKY_OBJ.encode())
+    objs = _compare_loaders(ren, p)
+    # the face before any `o` makes an anonymous mesh on material default0; the four named meshes all list material `first`
+    # first, whose corner list is shared between them (quad + triangle + pentagon fan + triangle + triangle = 24 corners)
+    assert [(m.vertices.shape[0], m.indices.shape[0]) for m, _ in objs] == [(3, 3), (24, 9), (24, 12), (24, 3), (24, 3)]
+    # the dragon stand-in through both parsers, with and without UVs, and with CRLF line ends
+    rows = scenes.dragon(700)
+    for k, with_uv in enumerate((False, True)):
+        q = tmp_path / f"dragon{k}.obj"
+        scenes.write_obj(str(q), rows, with_uv=with_uv)
+        _compare_loaders(ren, q)
+    crlf = tmp_path / "crlf.obj"
+    crlf.write_bytes((tmp_path / "dragon1.obj").read_bytes().replace(b"\n", b"\r\n"))
+    _compare_loaders(ren, crlf)
+    # malformed input raises, with the line number in the message
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 zero\nf 1 2 3\n")
+    with pytest.raises(Exception, match="line 3"):
+        ren.load_obj(str(bad))
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")
+    with pytest.raises(Exception, match="out of range"):
+        ren.load_obj(str(bad))
+    with pytest.raises(Exception, match="cannot open"):
+        ren.load_obj(str(tmp_path / "missing.obj"))
+    empty = tmp_path / "empty.obj"
+    empty.write_text("")
+    assert ren.load_obj(str(empty)) == []

@@ -169,6 +169,13 @@ int rt_dsl_compile(const char *cuda_source, uint64_t *out_module, char *log, int
 int rt_dsl_launch(uint64_t module, const char *kernel, int64_t n_threads, void **args, void *stream);
 int rt_dsl_unload(uint64_t module);
 
+/* Host only, no device work: where a draw with the tutorial vertex shaders (H = (((P, 1) World) View) Proj) can write.
+ * globals48 = World, View, Proj (the Transforms struct); [lo, hi] = bounding box of the mesh (3 doubles each).  Returns 1
+ * and the inclusive pixel rect of the eight projected corners +- 2 px clamped to the frame (x1 < x0: nothing on screen), or
+ * 0 when the box reaches the near plane (triangles get clipped) or the data is not finite.  A frame is the clear colour
+ * outside the union of its draws' rects: only that part has to be read back (rt_copy_rect). */
+int rt_raster_screen_bounds(const float *globals48, const double *lo, const double *hi, int width, int height, int *rect);
+
 /* ---- OBJ loading  (rendering/_loaders.py:7-33: pywavefront.Wavefront(path, collect_faces=True), then per mesh the first
  * material's interleaved, face-corner-expanded vertices) -- host code, no device work -----------------------------------
  * rt_obj_load parses the file (v / vn / vt / o / usemtl / f with v, v/t, v//n, v/t/n corners, 1-based or negative indices,

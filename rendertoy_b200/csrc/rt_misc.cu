@@ -1,4 +1,5 @@
 // rt_misc.cu -- error reporting, device info and mesh upload for librendertoy_b200.so.
+#include <math.h>
 #include <stdarg.h>
 
 #include "rt_common.cuh"
@@ -56,6 +57,42 @@ int rt_device_info(int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor)
     if (cc_major) RT_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc_minor) RT_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
     return RT_OK;
+}
+
+// Host only (no device work).  The tutorial vertex shaders place a vertex at H = (((P, 1) World) View) Proj and the
+// rasterizer turns that into the pixel ((H.x / H.w + 1) W / 2, (1 - H.y / H.w) H / 2) (_raster.py:118-133); a fragment's
+// pixel lies within one pixel of its triangle's screen bounding box (:239, :88-89).  So when every corner of the mesh's
+// bounding box [lo, hi] is in front of the near plane (z >= 0, w > 0: no triangle is clipped), everything a draw can write
+// lies in the rectangle of the eight projected corners: returned here, +- 2 px, clamped to the frame (possibly empty:
+// x1 < x0).  Returns 1, or 0 when there is no such bound (box reaches the near plane, non-finite data).
+// What it is for: a frame is the clear colour outside the union of its draws' rectangles, so only that part has to
+// be read back or gathered (Raster.content_rect).
+int rt_raster_screen_bounds(const float *globals48, const double *lo, const double *hi, int width, int height, int *rect)
+{
+    if (!globals48 || !lo || !hi || !rect || width <= 0 || height <= 0) return 0;
+    double smin = INFINITY, smax = -INFINITY, tmin = INFINITY, tmax = -INFINITY, wmax = 0.0, wmin = INFINITY;
+    for (int k = 0; k < 8; ++k) {
+        double v[4] = {(k & 4) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 1) ? hi[2] : lo[2], 1.0};
+        for (int m = 0; m < 3; ++m) {
+            const float *M = globals48 + 16 * m;
+            double r[4];
+            for (int j = 0; j < 4; ++j) r[j] = v[0] * M[j] + v[1] * M[4 + j] + v[2] * M[8 + j] + v[3] * M[12 + j];
+            v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3];
+        }
+        if (!(v[0] - v[0] == 0.0) || !(v[1] - v[1] == 0.0) || !(v[2] - v[2] == 0.0) || !(v[3] - v[3] == 0.0)) return 0;
+        if (!(v[2] > 0.0) || !(v[3] > 0.0)) return 0; // at or behind the near plane: clipping, no bound
+        const double s = v[0] / v[3], t = v[1] / v[3];
+        smin = s < smin ? s : smin; smax = s > smax ? s : smax; tmin = t < tmin ? t : tmin; tmax = t > tmax ? t : tmax;
+        wmax = v[3] > wmax ? v[3] : wmax; wmin = v[3] < wmin ? v[3] : wmin;
+    }
+    if (!(wmin > 1e-6 * wmax)) return 0; // float32 vertex arithmetic would not resolve this
+    const double big = 1073741824.0;
+    auto clampd = [&](double x) { return x < -big ? -big : (x > big ? big : x); };
+    const double px0 = clampd(floor((smin + 1.0) * (width * 0.5)) - 2.0), px1 = clampd(floor((smax + 1.0) * (width * 0.5)) + 3.0);
+    const double py0 = clampd(floor((1.0 - tmax) * (height * 0.5)) - 2.0), py1 = clampd(floor((1.0 - tmin) * (height * 0.5)) + 3.0);
+    rect[0] = px0 > 0.0 ? (int)px0 : 0; rect[1] = py0 > 0.0 ? (int)py0 : 0;
+    rect[2] = px1 < width - 1 ? (int)px1 : width - 1; rect[3] = py1 < height - 1 ? (int)py1 : height - 1;
+    return 1;
 }
 
 int rt_mesh_upload_soa(const void *d_mesh_vertices, int64_t n_vertices, void *d_pos4, void *d_nrm4, void *stream)

@@ -350,6 +350,26 @@ def mesh_soa(vertex_buffer):
     return hit[1], hit[2]
 
 
+def mesh_bounds(vertex_buffer):
+    """Bounding box of a MeshVertex buffer's positions as two (c_double * 3), cached per buffer version like the SoA
+    copy.  Costs one small reduction and a device->host read of 24 bytes (a sync) the first time a version is asked for."""
+    st = vertex_buffer._st
+    key = ("bounds", vertex_buffer.offset, vertex_buffer.size)
+    hit = st.cache.get(key)
+    if hit is None or hit[0] != st.version:
+        pos, _ = mesh_soa(vertex_buffer)
+        n = vertex_buffer.size
+        if n == 0:
+            lo = hi = [float("nan")] * 3
+        else:
+            xyz = pos[:n, :3]
+            both = torch.stack([xyz.amin(0), xyz.amax(0)]).double().cpu().tolist()
+            lo, hi = both
+        hit = (st.version, (ctypes.c_double * 3)(*lo), (ctypes.c_double * 3)(*hi))
+        st.cache[key] = hit
+    return hit[1], hit[2]
+
+
 def create_buffer(count: int, dtype: np.dtype):
     """Zero-filled device array (rendering/_core.py:13-14)."""
     dtype = np.dtype(dtype)

@@ -72,6 +72,7 @@ class Raster:
         self._depth_buffer = DepthView(self._key_buffer, n_pixels)
         self._fill_mode = FillMode.WIREFRAME
         self._keys_armed = False
+        self._draws = None      # draws since the last clear(render_target): [(vertex buffer, its version, globals)], None = unknown
 
         assert len(vertex_shader.signature) == 2 and vertex_shader.return_annotation is not None, "Vertex shader signature incorrect. Must receive one argument with vertex type and another with globals type, and return another struct"
         assert len(fragment_shader.signature) == 2 and fragment_shader.return_annotation == float4, "Fragment shader signature incorrect. Must receive one argument with fragment type and another with globals type, and return a float4"
@@ -145,6 +146,7 @@ class Raster:
         if depth_bits is not None:
             self._depth_buffer.fill(depth_bits)
         clear = rt.take_pending_clear()
+        self._draws = None      # user vertex shader: no bound on where it puts the mesh
         clear_px = 0
         if clear is not None:
             v = np.clip(np.array([clear[2], clear[1], clear[0], clear[3]], np.float32) * np.float32(255.0), 0, 255)
@@ -200,12 +202,50 @@ class Raster:
         if self._scratch is None or self._scratch.nbytes < need:
             self._scratch = create_buffer(need, np.uint8)
             self._scratch_tris = -1        # forces draw_triangles to size its own layout next time
+        gl, clear = self._vs_globals(), rt.take_pending_clear()
+        self._note_draw(vertex_buffer, gl, clear is not None)
         _native.call("rt_raster_draw_points", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
-                     self._vs_globals(), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
-                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, rt.take_pending_clear(),
+                     gl, self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
+                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, clear,
                      0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
         self._key_buffer.device_written()
         rt._buffer.device_written()
+
+    def _note_draw(self, vertex_buffer, globals48, new_frame):
+        """Book-keeping for content_rect (no device work, no sync): which mesh went in under which transforms since the
+        render target was last cleared."""
+        if new_frame:
+            self._draws = []
+        if self._draws is not None:
+            if len(self._draws) >= 64:
+                self._draws = None
+            else:
+                self._draws.append((vertex_buffer, vertex_buffer.version, globals48))
+
+    @property
+    def content_rect(self):
+        """Inclusive pixel rect (x0, y0, x1, y1) outside of which the render target holds the colour of the last
+        clear(render_target): the union, over the draws since that clear, of the screen rectangle of each mesh's bounding
+        box under the draw's World/View/Proj (rt_raster_screen_bounds).  The whole frame when that is not known: user
+        vertex shaders, a mesh reaching the near plane, a vertex buffer modified since it was drawn, no clear yet.
+        (x1 < x0: nothing was drawn on screen.)  Not part of the reference API; it is what lets a frame be read back or
+        gathered sparsely (parallel.SparseFrameCopier).  The first query for a mesh version reads its bounds back (a sync)."""
+        import ctypes
+        W, H = self._render_target.width, self._render_target.height
+        full = (0, 0, W - 1, H - 1)
+        if self._draws is None:
+            return full
+        x0, y0, x1, y1 = W, H, -1, -1
+        r = (ctypes.c_int * 4)()
+        for vb, version, gl in self._draws:
+            if vb.version != version:
+                return full
+            lo, hi = _core.mesh_bounds(vb)
+            if not _native.lib().rt_raster_screen_bounds(gl, lo, hi, W, H, r):
+                return full
+            if r[2] >= r[0] and r[3] >= r[1]:
+                x0, y0, x1, y1 = min(x0, r[0]), min(y0, r[1]), max(x1, r[2]), max(y1, r[3])
+        return (x0, y0, x1, y1) if x1 >= x0 else (0, 0, -1, -1)
 
     def _vs_globals(self):
         """48 floats (World, View, Proj) as a ctypes array: the Transforms struct is three contiguous float4x4 (layout
@@ -241,9 +281,11 @@ class Raster:
             need = _native.lib().rt_raster_scratch_bytes(self.shader_id, primitive_count, rt.width, rt.height)
             self._scratch = create_buffer(int(need), np.uint8)   # zero-filled: the control block starts armed
             self._scratch_tris = primitive_count
+        gl, clear = self._vs_globals(), rt.take_pending_clear()
+        self._note_draw(vertex_buffer, gl, clear is not None)
         _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
-                     self._vs_globals(), self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
-                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, rt.take_pending_clear(),
+                     gl, self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
+                     self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, clear,
                      0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
         self._key_buffer.device_written()
         rt._buffer.device_written()

@@ -348,3 +348,30 @@ def test_native_obj_parser_matches_python_formulation(ren, tmp_path):
     empty = tmp_path / "empty.obj"
     empty.write_text("")
     assert ren.load_obj(str(empty)) == []
+
+
+def test_raster_screen_bounds_native(ren):
+    """rt_raster_screen_bounds (host-only C): rectangle of the projected mesh box against a float64 NumPy projection of the
+    same corners; no bound when the box reaches the near plane."""
+    import ctypes
+    L = _native.lib()
+    lo, hi = np.array([-0.5, -0.31, -0.22]), np.array([0.5, 0.27, 0.24])
+    clo, chi = (ctypes.c_double * 3)(*lo), (ctypes.c_double * 3)(*hi)
+    corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+    for k in range(48):
+        W, H = [(1920, 1080), (333, 211)][k % 2]
+        mats = [ren.to_array(np.array(m, dtype=ren.float4x4)).astype(np.float32) for m in scenes.lesson_camera(ren, 8 if k % 3 else 6, 0.41 * k, W, H)]
+        g = np.concatenate([m.ravel() for m in mats]).astype(np.float32)
+        rect = (ctypes.c_int * 4)()
+        ok = L.rt_raster_screen_bounds(g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), clo, chi, W, H, rect)
+        h4 = corners @ mats[0].astype(np.float64) @ mats[1].astype(np.float64) @ mats[2].astype(np.float64)
+        assert ok == 1 and (h4[:, 2] > 0).all()
+        px = (h4[:, 0] / h4[:, 3] + 1.0) * W / 2
+        py = (1.0 - h4[:, 1] / h4[:, 3]) * H / 2
+        want = (max(0, int(np.floor(px.min())) - 2), max(0, int(np.floor(py.min())) - 2),
+                min(W - 1, int(np.floor(px.max())) + 3), min(H - 1, int(np.floor(py.max())) + 3))
+        assert tuple(rect) == want
+    from oracle import host_math as hm
+    g = np.concatenate([m.ravel() for m in (hm.rotate(4.5, (0, 1, 0)), hm.look_at((0.12, 0.32, 0.3), (0, 0, 0), (0, 1, 0)),
+                                            hm.perspective(aspect_ratio=16 / 9))]).astype(np.float32)
+    assert L.rt_raster_screen_bounds(g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), clo, chi, 640, 360, (ctypes.c_int * 4)()) == 0

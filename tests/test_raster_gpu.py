@@ -21,6 +21,13 @@ def _compare(raster, result, label):
     assert covered > 0
 
 
+def _upload(ren, rows):
+    vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[:] = rows
+    return vb
+
+
 def _texture(seed=3, w=50, h=37):
     rng = np.random.default_rng(seed)
     return rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
@@ -111,3 +118,52 @@ def test_draw_points_matches_oracle(ren, oracle, lesson, indexed):
     raster.draw_triangles(vb, None)
     res2 = oracle.draw_triangles(lesson, w, h, rows, lessons.globals_as_floats(g), texture=texf, depth=res.depth, bgra=res.bgra)
     _compare(raster, res2, "points then triangles")
+
+
+def test_content_rect_holds_everything_drawn(ren):
+    """Raster.content_rect: outside it the render target is the clear colour (the contract of the sparse read-back)."""
+    import torch
+    from oracle import host_math as hm
+    w, h = 640, 360
+    rows = scenes.dragon(6000)
+    vb = _upload(ren, rows)
+    small = rows.copy()
+    small[:, 0:3] = small[:, 0:3] * np.float32(0.3) + np.float32([0.6, 0.2, 0.0])
+    vb2 = _upload(ren, small)
+    pres = ren.create_presenter(w, h)
+    raster, g = lessons.build_lesson08(ren, pres.get_render_target())
+    assert raster.content_rect == (0, 0, w - 1, h - 1)                      # nothing known yet
+
+    def check(rect):
+        img = raster.get_render_target().get().view(np.uint32).reshape(h, w)
+        assert img.any()
+        outside = np.ones((h, w), bool)
+        if rect[2] >= rect[0]:
+            outside[rect[1]:rect[3] + 1, rect[0]:rect[2] + 1] = False
+        assert not img[outside].any(), "pixels drawn outside content_rect"
+
+    for lesson, t in [(6, 0.4), (8, 1.9), (6, 3.3)]:
+        lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, lesson, t, w, h))
+        raster.get_render_target().buffer.tensor().fill_(0x77)              # stale pixels everywhere
+        lessons.render_frame(ren, raster, vb)
+        r1 = raster.content_rect
+        assert r1 != (0, 0, w - 1, h - 1) and r1[2] > r1[0]
+        check(r1)
+        raster.draw_triangles(vb2, None)                                      # second draw of the frame: the union
+        r2 = raster.content_rect
+        assert r2[0] <= r1[0] and r2[1] <= r1[1] and r2[2] >= r1[2] and r2[3] >= r1[3]
+        check(r2)
+        raster.draw_points(vb2)
+        check(raster.content_rect)
+    # the camera inside the mesh: triangles are clipped, no bound
+    W, V, P = hm.rotate(4.5, (0, 1, 0)), hm.look_at((0.12, 0.32, 0.3), (0, 0, 0), (0, 1, 0)), hm.perspective(aspect_ratio=w / h)
+    lessons.set_transforms(ren, g, *(ren.make_float4x4(np.ascontiguousarray(x)) for x in (W, V, P)))
+    lessons.render_frame(ren, raster, vb)
+    assert raster.content_rect == (0, 0, w - 1, h - 1)
+    # a vertex buffer written after it was drawn: unknown again
+    lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8, 0.5, w, h))
+    lessons.render_frame(ren, raster, vb)
+    assert raster.content_rect != (0, 0, w - 1, h - 1)
+    with ren.mapped(vb) as m:
+        m.view(np.float32).reshape(rows.shape)[0, 0] += 0.0
+    assert raster.content_rect == (0, 0, w - 1, h - 1)

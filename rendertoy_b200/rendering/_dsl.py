@@ -81,7 +81,8 @@ def program_source(kernel):
     uses_textures = any("sample2D" in f.source for f in functions) or "sample2D" in kernel.body
     if uses_textures:
         parts.append(f"__device__ const unsigned long long memory_pool_ptr = {pool.get_buffer().ptr}ull;\n"
-                     "#define sample2D(texture, c) cl_sample2D(memory_pool_ptr, (texture), (c))\n")
+                     "#define sample2D(texture, c) cl_sample2D(memory_pool_ptr, (texture), (c))\n"
+                     "#define sample2D_linear(texture, c) cl_sample2D_linear(memory_pool_ptr, (texture), (c))\n")
     for name, dt in _core._STRUCTS.items():
         fields = "\n".join(f"    {_core.dtype_cname(dt.fields[n][0])} {n};" for n in dt.names)
         parts.append(f"struct {name} {{\n{fields}\n}};\nstatic_assert(sizeof({name}) == {dt.itemsize}, \"{name}: layout differs from the host dtype\");\n")
@@ -130,7 +131,8 @@ def raster_program_source(vertex_shader, fragment_shader, vin, vout, vsg, fsg):
     functions = _reachable_functions(f"{vertex_shader.name}( {fragment_shader.name}(")
     if any("sample2D" in f.source for f in functions):
         parts.append(f"__device__ const unsigned long long memory_pool_ptr = {_core.__MEMORY_POOL__.get_buffer().ptr}ull;\n"
-                     "#define sample2D(texture, c) cl_sample2D(memory_pool_ptr, (texture), (c))\n")
+                     "#define sample2D(texture, c) cl_sample2D(memory_pool_ptr, (texture), (c))\n"
+                     "#define sample2D_linear(texture, c) cl_sample2D_linear(memory_pool_ptr, (texture), (c))\n")
     for name, dt in _core._STRUCTS.items():
         fields = "\n".join(f"    {_core.dtype_cname(dt.fields[n][0])} {n};" for n in dt.names)
         parts.append(f"struct {name} {{\n{fields}\n}};\nstatic_assert(sizeof({name}) == {dt.itemsize}, \"{name}: layout differs from the host dtype\");\n")

@@ -203,6 +203,26 @@ __device__ inline clf4 cl_sample2D(unsigned long long pool, const TEX &t, const 
     return ((const clf4 *)(pool + (unsigned long long)t.offset))[row * t.width + col];
 }
 
+// sample2D_linear: the bilinear sampler docs/09_texture_mapping.md:69-70 asks for ("would be another function, like
+// sample2D_linear"); the reference never got it.  Same repeat wrap as sample2D, texel centres at (i + 0.5) / size (so a
+// coordinate that sample2D maps to the middle of a texel returns exactly that texel), neighbours wrap around the edges,
+// weights and blends in float32 as written.
+template <typename TEX>
+__device__ inline clf4 cl_sample2D_linear(unsigned long long pool, const TEX &t, const clf2 &c)
+{
+    const float x = wrap_coord(c.x) * t.width - 0.5f, y = wrap_coord(c.y) * t.height - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    int c0 = (int)fx, r0 = (int)fy;
+    c0 = c0 < 0 ? c0 + t.width : (c0 >= t.width ? c0 - t.width : c0);
+    r0 = r0 < 0 ? r0 + t.height : (r0 >= t.height ? r0 - t.height : r0);
+    const int c1 = c0 + 1 >= t.width ? 0 : c0 + 1, r1 = r0 + 1 >= t.height ? 0 : r0 + 1;
+    const clf4 *tex = (const clf4 *)(pool + (unsigned long long)t.offset);
+    const clf4 t00 = tex[r0 * t.width + c0], t01 = tex[r0 * t.width + c1], t10 = tex[r1 * t.width + c0], t11 = tex[r1 * t.width + c1];
+    const clf4 top = t00 * (1.0f - ax) + t01 * ax, bottom = t10 * (1.0f - ax) + t11 * ax;
+    return top * (1.0f - ay) + bottom * ay;
+}
+
 #define __kernel
 #define __global
 #define __constant const

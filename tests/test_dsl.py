@@ -207,3 +207,62 @@ def test_lesson07_parametric_transform(ren, kernels):
     exp = np.stack([p[:, 0] * c + p[:, 2] * s, p[:, 1], -p[:, 0] * s + p[:, 2] * c], axis=1)
     assert np.allclose(after[:, 0:3], exp, atol=2e-5)
     assert np.array_equal(after[:, 4:], before[:, 4:])
+
+
+@pytest.fixture(scope="module")
+def linear_kernel(ren):
+    @ren.kernel_struct
+    class LinearSampleInfo:
+        Tex: ren.Texture2D
+
+    @ren.kernel_main
+    def sample_both(nearest: [ren.float4], linear: [ren.float4], coords: [ren.float2], info: LinearSampleInfo):
+        """
+        nearest[thread_id] = sample2D(info.Tex, coords[thread_id]);
+        linear[thread_id] = sample2D_linear(info.Tex, coords[thread_id]);
+        """
+    return LinearSampleInfo, sample_both
+
+
+def test_sample2D_linear_compiles(ren, linear_kernel):
+    from rendering import _dsl
+    ren.create_texture2D(4, 4)      # the program bakes the pool address in: the pool must exist
+    assert _dsl.compile_program(_dsl.program_source(linear_kernel[1])) != 0
+
+
+@pytest.mark.gpu
+def test_sample2D_linear_against_numpy(ren, linear_kernel):
+    """sample2D_linear (the bilinear sampler docs/09 asks for): texel centres at (i + 0.5) / size, repeat wrap."""
+    info_t, kernel = linear_kernel
+    rng = np.random.default_rng(5)
+    tw, th = 7, 5
+    tex = rng.random((th, tw, 4), dtype=np.float32)
+    mem, desc = ren.create_texture2D(tw, th)
+    with ren.mapped(mem) as m:
+        m.view(np.float32).ravel().reshape(th, tw, 4)[:] = tex
+    info = ren.create_struct(info_t)
+    with ren.mapped(info) as m:
+        m["Tex"] = desc.get()
+    n = 4096
+    uv = rng.uniform(-2.5, 2.5, (n, 2)).astype(np.float32)
+    uv[:tw * th, 0] = (np.arange(tw * th) % tw + 0.5) / tw                   # texel centres: linear == nearest == the texel
+    uv[:tw * th, 1] = (np.arange(tw * th) // tw + 0.5) / th
+    cb = ren.create_buffer(n, ren.float2)
+    with ren.mapped(cb) as m:
+        m.view(np.float32).reshape(n, 2)[:] = uv
+    near, lin = ren.create_buffer(n, ren.float4), ren.create_buffer(n, ren.float4)
+    kernel[n](near, lin, cb, info)
+    near, lin = near.get().view(np.float32).reshape(n, 4), lin.get().view(np.float32).reshape(n, 4)
+    f32 = np.float32
+    wrap = lambda c: np.fmod(np.fmod(c, f32(1)) + f32(1), f32(1)).astype(f32)
+    x, y = wrap(uv[:, 0]) * f32(tw) - f32(0.5), wrap(uv[:, 1]) * f32(th) - f32(0.5)
+    fx, fy = np.floor(x), np.floor(y)
+    ax, ay = (x - fx).astype(f32)[:, None], (y - fy).astype(f32)[:, None]
+    c0, r0 = fx.astype(int) % tw, fy.astype(int) % th
+    c1, r1 = (c0 + 1) % tw, (r0 + 1) % th
+    top = tex[r0, c0] * (f32(1) - ax) + tex[r0, c1] * ax
+    bottom = tex[r1, c0] * (f32(1) - ax) + tex[r1, c1] * ax
+    want = top * (f32(1) - ay) + bottom * ay
+    assert np.allclose(lin, want, atol=1e-6)
+    k = tw * th
+    assert np.allclose(lin[:k], tex.reshape(-1, 4), atol=1e-6) and np.array_equal(near[:k], tex.reshape(-1, 4))

@@ -301,16 +301,26 @@ def bench_raycast(args, rank, world):
     e2e_targets = targets if not fused else [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
 
     def e2e_step(s):
+        # like the device-resident loop, the frames of a batch alternate over the ray-cast streams; one copy stream
+        if ray_streams is not None:
+            for st in ray_streams:
+                st.wait_stream(main_stream)
         for j, k in enumerate(my_frames):
             world_m, view, proj = scenes.lesson_camera(ren, 6, orbit_t(s * n_frames + k), RAY_W, RAY_H)   # host inputs
             cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world_m, dtype=ren.float4x4))
+            if ray_streams is not None:
+                torch.cuda.set_stream(ray_streams[j % len(ray_streams)])
             content = rc.render(e2e_targets[j], cam)
             done[j % 2].record()
             copy_stream.wait_event(done[j % 2])
             # the frame is the clear colour outside `content`, and so is the (initially cleared) host frame outside the
             # content of the frame it held before: one pitched D2H copy of the union makes the host frame complete
             reader.copy(j % 2, host[j % 2].data_ptr(), e2e_targets[j].ptr, content if args.sparse_readback else full_rect, copy_ptr)
-        torch.cuda.current_stream().wait_stream(copy_stream)
+        if ray_streams is not None:
+            torch.cuda.set_stream(main_stream)
+            for st in ray_streams:
+                main_stream.wait_stream(st)
+        main_stream.wait_stream(copy_stream)
 
     e2e_step(0)
     barrier_sync(world)

@@ -13,7 +13,6 @@ oracle/raycast_oracle.c (float32 Moller-Trumbore, closest hit by (t bits, triang
                  written straight into a render target (Lambert of lesson08:42 or texture of lesson09:90-95)
 """
 import ctypes
-import math
 import typing
 
 import numpy as np

@@ -122,7 +122,6 @@ def test_draw_points_matches_oracle(ren, oracle, lesson, indexed):
 
 def test_content_rect_holds_everything_drawn(ren):
     """Raster.content_rect: outside it the render target is the clear colour (the contract of the sparse read-back)."""
-    import torch
     from oracle import host_math as hm
     w, h = 640, 360
     rows = scenes.dragon(6000)

@@ -92,7 +92,10 @@ def _parse_obj(path):
 
 
 def _normalise_positions(rows):
-    """The reference's scalar min/max normalisation (_loaders.py:34-38), float32."""
+    """The reference's scalar min/max normalisation (_loaders.py:34-38), float32.  (A mesh whose first material never got
+    a face has no rows: nothing to do; the reference's min() would raise on it.)"""
+    if rows.shape[0] == 0:
+        return
     v_min = rows[:, 0:3].min()
     v_max = rows[:, 0:3].max()
     v_size = v_max - v_min
@@ -117,7 +120,7 @@ def load_obj(path):
             mesh_vertices = create_buffer(nv.value, MeshVertex)
             mesh_indices = create_buffer(nf.value * 3, int)
             with mapped(mesh_vertices) as map:
-                rows = map.view(np.float32).reshape(nv.value, -1)
+                rows = map.view(np.float32).reshape(nv.value, MeshVertex.itemsize // 4)
                 if L.rt_obj_mesh_rows(handle, i, rows.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), rows.shape[1]) != 0:
                     raise Exception(f"load_obj({path!r}): {L.rt_last_error().decode(errors='replace')}")
                 _normalise_positions(rows)
@@ -140,8 +143,8 @@ def _load_obj_python(path):
         mesh_vertices = create_buffer(vertex_count, MeshVertex)
         mesh_indices = create_buffer(m.n_faces * 3, int)
         with mapped(mesh_vertices) as map:
-            rows = map.view(np.float32).reshape(vertex_count, -1)
-            for att in mat.vertex_format.split('_'):
+            rows = map.view(np.float32).reshape(vertex_count, MeshVertex.itemsize // 4)
+            for att in (mat.vertex_format or 'V3F').split('_'):     # a material without faces has no format yet
                 if att == 'N3F':
                     rows[:, 4:7] = nrm[c[:, 2]]
                 elif att == 'V3F':

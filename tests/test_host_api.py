@@ -375,3 +375,56 @@ def test_raster_screen_bounds_native(ren):
     g = np.concatenate([m.ravel() for m in (hm.rotate(4.5, (0, 1, 0)), hm.look_at((0.12, 0.32, 0.3), (0, 0, 0), (0, 1, 0)),
                                             hm.perspective(aspect_ratio=16 / 9))]).astype(np.float32)
     assert L.rt_raster_screen_bounds(g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), clo, chi, 640, 360, (ctypes.c_int * 4)()) == 0
+
+
+def _random_obj(rng):
+    """A random but valid OBJ text touching every rule of the loader: all four corner formats (fixed per material by its
+    first corner, later faces may differ), negative indices, polygons, several `o` / `usemtl`, ignored statements, odd
+    number spellings, tabs, trailing blanks, CRLF."""
+    def num():
+        x = float(rng.normal()) * 10.0 ** int(rng.integers(-3, 4))
+        style = int(rng.integers(0, 6))
+        return [f"{x:.9g}", f"{x:.3f}", f"{x:e}", f"{x:+.5g}", repr(x), f"{int(x)}"][style]
+    lines, nv, nt, nn = [], 0, 0, 0
+    eol = "\r\n" if rng.random() < 0.3 else "\n"
+    sep = lambda: " " * int(rng.integers(1, 3)) if rng.random() < 0.8 else "\t"
+    def emit(*toks):
+        lines.append(sep().join(toks) + (" " if rng.random() < 0.1 else ""))
+    for _ in range(int(rng.integers(3, 9))):
+        emit("v", num(), num(), num()); nv += 1
+    emit("vt", num(), num()); nt += 1
+    emit("vn", num(), num(), num()); nn += 1
+    for _ in range(int(rng.integers(4, 40))):
+        kind = rng.random()
+        if kind < 0.25:
+            emit("v", num(), num(), num(), *([num()] if rng.random() < 0.2 else [])); nv += 1
+        elif kind < 0.35:
+            emit("vt", num(), *([num()] if rng.random() < 0.8 else [])); nt += 1
+        elif kind < 0.45:
+            emit("vn", num(), num(), num()); nn += 1
+        elif kind < 0.52:
+            emit("o", f"mesh{int(rng.integers(0, 5))}")
+        elif kind < 0.60:
+            emit("usemtl", *([f"mat{int(rng.integers(0, 4))}"] if rng.random() < 0.9 else []))
+        elif kind < 0.68:
+            emit(str(rng.choice(["g grp", "s 1", "mtllib x.mtl", "# note", "l 1 2", ""])))
+        else:
+            fmt = int(rng.integers(0, 4))
+            corners = []
+            for _ in range(int(rng.integers(3, 7))):
+                def idx(count):
+                    return str(int(rng.integers(1, count + 1))) if rng.random() < 0.7 else str(-int(rng.integers(1, count + 1)))
+                v, t, n = idx(nv), idx(nt), idx(nn)
+                corners.append([v, f"{v}/{t}", f"{v}//{n}", f"{v}/{t}/{n}"][fmt])
+            emit("f", *corners)
+    return eol.join(lines) + (eol if rng.random() < 0.8 else "")
+
+
+def test_native_obj_parser_fuzz(ren, tmp_path):
+    rng = np.random.default_rng(2024)
+    p = tmp_path / "fuzz.obj"
+    meshes = 0
+    for _ in range(150):
+        p.write_bytes(_random_obj(rng).encode())
+        meshes += len(_compare_loaders(ren, p))
+    assert meshes > 100

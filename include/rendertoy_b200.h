@@ -145,6 +145,10 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * against screen rectangles instead of rays against boxes -- same hits, fewer instructions per node.  The scratch is
  * per call: concurrent calls on different streams need different buffers. */
 int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
+/* EXPERIMENTAL, off by default, not yet measured: after the projection, run `passes` (0..64) in-place passes that tighten
+ * every inner child's screen rectangle and depth bound to the union of that child's own two (rt_raycast.cu:
+ * view_refit_kernel).  Hits cannot change.  Process-wide setting. */
+int rt_raycast_set_view_refit(int passes);
 /* Host only, no device work: the cull_rect for rt_raycast_primary -- conservative inclusive pixel rect of the scene box
  * [lo, hi] (3 doubles each) under `camera`, projected corners +- 2 px clamped to the frame.  Returns 1 and fills rect[4],
  * or 0 when there is no usable bound (box reaches the eye plane, singular camera basis, non-finite data): pass NULL then. */

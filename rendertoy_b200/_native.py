@@ -37,6 +37,7 @@ SIGNATURES = {
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
                                      _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),
     "rt_raycast_view_node_bytes": (_I64, [_I64]),
+    "rt_raycast_set_view_refit": (C.c_int, [_I32]),
     "rt_camera_frame": (C.c_int, [_FP, _FP, _FP, _FP]),
     "rt_raycast_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),

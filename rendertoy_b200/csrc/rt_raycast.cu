@@ -150,6 +150,41 @@ __global__ void __launch_bounds__(128) project_kernel(const ProjectArgs p)
     p.vnodes[i] = v;
 }
 
+// EXPERIMENTAL, OFF BY DEFAULT, NOT YET RUN ON A GPU (written after the round's GPU budget was spent; see DESIGN.md section 8
+// and tools/refit_experiment.py for the CPU estimate: -25 % node visits per tile packet with 4 passes, -32 % converged).
+// project_kernel gives an inner child the rectangle of its projected 3-D box.  The union of that child's own two
+// rectangles -- which end, at the leaves, in triangle-tight rectangles -- is never larger and for slanted geometry much
+// smaller, likewise the nearer of their depth bounds.  One pass tightens every node from its children's current values, in
+// place.  That is safe without any ordering or atomicity: a rectangle component only ever moves inwards and a depth bound only
+// up, each stays a valid bound at every moment, so whatever mix of old and new values a thread reads gives a valid (if
+// looser) result.  PLOC hands node ids out downwards (children have larger ids than their parents), so the thread -> node
+// mapping is reversed: the blocks scheduled first hold the deepest nodes and one pass usually carries tightness up several
+// levels.  Hits cannot change: every leaf rectangle is untouched and every ancestor keeps containing it.
+__global__ void __launch_bounds__(128) view_refit_kernel(ViewNode *v, long long n_inner)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_inner) return;
+    float4 *me = reinterpret_cast<float4 *>(v + (n_inner - 1 - t));
+    float4 r[2] = {__ldcg(me), __ldcg(me + 1)};
+    float4 zc = __ldcg(me + 2);
+    const int child[2] = {__float_as_int(zc.z), __float_as_int(zc.w)};
+    float z[2] = {zc.x, zc.y};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (child[c] < 0) continue; // a leaf: already the triangle's rectangle
+        const float4 *cp = reinterpret_cast<const float4 *>(v + child[c]);
+        const float4 a = __ldcg(cp), b = __ldcg(cp + 1), cz = __ldcg(cp + 2);
+        // fminf / fmaxf drop NaN; an empty rectangle is (inf, -inf, inf, -inf) and an unbounded one (-inf, inf, -inf, inf)
+        r[c].x = fmaxf(r[c].x, fminf(a.x, b.x)); r[c].y = fminf(r[c].y, fmaxf(a.y, b.y));
+        r[c].z = fmaxf(r[c].z, fminf(a.z, b.z)); r[c].w = fminf(r[c].w, fmaxf(a.w, b.w));
+        z[c] = fmaxf(z[c], fminf(cz.x, cz.y));
+    }
+    me[0] = r[0]; me[1] = r[1];
+    me[2] = make_float4(z[0], z[1], zc.z, zc.w);
+}
+
+int g_view_refit_passes = 0; // rt_raycast_set_view_refit
+
 struct TraceArgs {
     const RtBvhNode *nodes;
     const RtBvhTri *tris;
@@ -551,6 +586,9 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
             p.tris = a.tris; // leaf rectangles from the triangles themselves (189 -> 169 us per cfg4 frame against box rectangles)
             project_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
             RT_CUDA(cudaGetLastError());
+            for (int k = 0; k < g_view_refit_passes; ++k) // experimental, 0 by default
+                view_refit_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p.vnodes, p.n_inner);
+            RT_CUDA(cudaGetLastError());
             a.vnodes = p.vnodes;
         }
     }
@@ -659,6 +697,15 @@ int rt_raycast_screen_bounds(const float *camera, const double *lo, const double
     rect[0] = px0 > 0.0 ? (int)px0 : 0; rect[1] = py0 > 0.0 ? (int)py0 : 0;
     rect[2] = px1 < width - 1 ? (int)px1 : width - 1; rect[3] = py1 < height - 1 ? (int)py1 : height - 1;
     return 1;
+}
+
+// EXPERIMENTAL (see view_refit_kernel): number of tightening passes rt_raycast_primary runs after the projection, 0..64.
+// Process-wide; 0 (the default) leaves the measured path exactly as it is.
+int rt_raycast_set_view_refit(int passes)
+{
+    RT_REQUIRE(passes >= 0 && passes <= 64, "0..64 passes");
+    g_view_refit_passes = passes;
+    return RT_OK;
 }
 
 int64_t rt_raycast_view_node_bytes(int64_t n_triangles)

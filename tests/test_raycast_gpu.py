@@ -1,5 +1,7 @@
 """GPU parity: rendering._raycaster.Raycaster (LBVH build + traversal + shade, native sm_100a) vs the oracle's
 brute-force float32 Moller-Trumbore definition (small scenes) and its CPU BVH (full-size scenes)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -383,3 +385,32 @@ def test_frame_store_sparse_push(ren):
         assert 0 < moved < 0.7 * 12 * w * h * 4
     finally:
         store.close()
+
+
+@pytest.mark.skipif(os.environ.get("RENDERTOY_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental view-node refit: written after the round's GPU budget was spent, not yet run on a GPU")
+def test_experimental_view_refit_keeps_hits(ren):
+    """rt_raycast_set_view_refit(k): tightening passes over the screen-space nodes must not change a single hit record."""
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200 import _native
+    rows = scenes.dragon(30_000)
+    w, h = 1280, 720
+    try:
+        for builder in ("ploc", "lbvh"):
+            rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)], builder=builder)
+            for lesson, t in [(6, 0.5), (8, 2.2), (6, 4.1)]:
+                cam = _camera(ren, lesson, t, w, h)
+                ref = torch.empty((w * h, 4), dtype=torch.float32, device="cuda")
+                _native.call("rt_raycast_set_view_refit", 0)
+                st0 = torch.zeros(3, dtype=torch.int64, device="cuda")
+                rc.render(None, cam, hits=ref, frame_size=(w, h), stats=st0)
+                for passes in (1, 2, 4, 16):
+                    _native.call("rt_raycast_set_view_refit", passes)
+                    got = torch.empty_like(ref)
+                    st = torch.zeros(3, dtype=torch.int64, device="cuda")
+                    rc.render(None, cam, hits=got, frame_size=(w, h), stats=st)
+                    assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), f"{builder}, {passes} passes: hits changed"
+                    assert int(st[0]) <= int(st0[0]), "tightening cannot add node visits"
+                    print(builder, lesson, passes, "node visits", int(st0[0]), "->", int(st[0]))
+    finally:
+        _native.call("rt_raycast_set_view_refit", 0)

@@ -33,6 +33,11 @@ def run(n_tris, w, h, lesson, frames=20):
     print(f"T={rows.shape[0]//3} {w}x{h} lesson{lesson:02d}: build {e0.elapsed_time(e1)*1e3:.0f} us (first {tb*1e3:.1f} ms), render {ms*1e3:.1f} us/frame -> {w*h/ms/1e3:.1f} Mrays/s, coverage {cov:.3f}")
 
 if __name__ == "__main__":
+    import os
+    if os.environ.get("RT_VIEW_REFIT"):      # experimental tightening passes (rt_raycast_set_view_refit), A/B by hand
+        from rendertoy_b200 import _native
+        _native.call("rt_raycast_set_view_refit", int(os.environ["RT_VIEW_REFIT"]))
+        print("view refit passes:", os.environ["RT_VIEW_REFIT"])
     fr = 3 if len(sys.argv) > 1 and sys.argv[1] == "ncu" else 20
     run(100_000, 3840, 2160, 6, fr); sys.stdout.flush()
     run(100_000, 3840, 2160, 8, fr)

@@ -410,7 +410,8 @@ def test_experimental_view_refit_keeps_hits(ren):
                     st = torch.zeros(3, dtype=torch.int64, device="cuda")
                     rc.render(None, cam, hits=got, frame_size=(w, h), stats=st)
                     assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), f"{builder}, {passes} passes: hits changed"
-                    assert int(st[0]) <= int(st0[0]), "tightening cannot add node visits"
+                    # (not strictly monotone: tighter depth bounds can swap the visiting order of two children)
+                    assert int(st[0]) <= 1.02 * int(st0[0]), "tightening should not add node visits"
                     print(builder, lesson, passes, "node visits", int(st0[0]), "->", int(st[0]))
     finally:
         _native.call("rt_raycast_set_view_refit", 0)

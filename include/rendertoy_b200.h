@@ -149,6 +149,10 @@ int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
  * every inner child's screen rectangle and depth bound to the union of that child's own two (rt_raycast.cu:
  * view_refit_kernel).  Hits cannot change.  Process-wide setting. */
 int rt_raycast_set_view_refit(int passes);
+/* EXPERIMENTAL, off by default, not yet measured: a_max_tiles > 0 makes rt_raycast_primary's screen-space path walk the top
+ * of the tree once per 64 x 16-pixel region (frontier of nodes at most a_max_tiles 8x4-pixel tiles in area, in shared
+ * memory) and only the rest per tile (rt_raycast.cu: raycast_region_kernel).  Hits cannot change.  0 = off.  Process-wide. */
+int rt_raycast_set_region_traversal(float a_max_tiles);
 /* Host only, no device work: the cull_rect for rt_raycast_primary -- conservative inclusive pixel rect of the scene box
  * [lo, hi] (3 doubles each) under `camera`, projected corners +- 2 px clamped to the frame.  Returns 1 and fills rect[4],
  * or 0 when there is no usable bound (box reaches the eye plane, singular camera basis, non-finite data): pass NULL then. */

@@ -38,6 +38,7 @@ SIGNATURES = {
                                      _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),
     "rt_raycast_view_node_bytes": (_I64, [_I64]),
     "rt_raycast_set_view_refit": (C.c_int, [_I32]),
+    "rt_raycast_set_region_traversal": (C.c_int, [C.c_float]),
     "rt_camera_frame": (C.c_int, [_FP, _FP, _FP, _FP]),
     "rt_raycast_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),

@@ -413,5 +413,19 @@ def test_experimental_view_refit_keeps_hits(ren):
                     # (not strictly monotone: tighter depth bounds can swap the visiting order of two children)
                     assert int(st[0]) <= 1.02 * int(st0[0]), "tightening should not add node visits"
                     print(builder, lesson, passes, "node visits", int(st0[0]), "->", int(st[0]))
+                # the two-level region traversal, alone and on top of the refit
+                for a_max, passes in ((8.0, 0), (2.0, 0), (64.0, 4), (8.0, 4), (0.001, 0)):
+                    _native.call("rt_raycast_set_view_refit", passes)
+                    _native.call("rt_raycast_set_region_traversal", a_max)
+                    got = torch.empty_like(ref)
+                    img = ren.create_image2d(w, h, ren._core.RGBA)
+                    rc.render(img, cam, hits=got)
+                    _native.call("rt_raycast_set_region_traversal", 0.0)
+                    assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), f"{builder}, region traversal a_max={a_max}: hits changed"
+                    _native.call("rt_raycast_set_view_refit", 0)
+                    base = ren.create_image2d(w, h, ren._core.RGBA)
+                    rc.render(base, cam)
+                    assert np.array_equal(img.get(), base.get()), "region traversal: shaded frame differs"
     finally:
         _native.call("rt_raycast_set_view_refit", 0)
+        _native.call("rt_raycast_set_region_traversal", 0.0)

@@ -1,0 +1,17 @@
+"""CPU: the SOURCE of csrc/rt_raycast.cu executed on host threads (tools/cuda_emu: one std::thread per CUDA thread, barriers
+for __syncthreads and the warp collectives) against the oracle's brute-force definition, bit for bit.  Covers the measured
+screen-space packet walk, the per-lane 3-D walk and the two experimental variants (refit passes, two-level region traversal
+with and without overflow of its shared arrays).  Kernel logic only; the B200 parity suite is tests/*_gpu.py."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(600)
+def test_raycast_kernels_on_the_cpu_emulator():
+    sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+    import check_raycast
+    assert check_raycast.main(600, 64, 32) == 0

@@ -1,0 +1,116 @@
+"""tools/cuda_emu/check_raycast.py -- DEV-TIME TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+    python tools/cuda_emu/check_raycast.py [n_tris] [width height]
+
+Runs the source of csrc/rt_raycast.cu on CPU threads (tools/cuda_emu) over a numpy-built PLOC tree in the library's node /
+leaf layout and compares every hit record and shaded pixel with the oracle's brute-force definition, bit for bit, for: the
+measured screen-space packet walk, the experimental refit passes, the experimental two-level region traversal (several
+frontier thresholds, including one that overflows the shared arrays and must fall back), and the per-lane 3-D walk.
+This checks kernel LOGIC only -- it is how code written without GPU time left gets its first run.
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, HERE)
+os.environ.setdefault("RENDERTOY_B200_HOST_BUFFERS", "1")
+
+
+def library_bvh(rows):
+    """PLOC tree (tools/refit_experiment.ploc) in rt_bvh.cuh layout: root 0, children with larger ids, leaf = ~slot."""
+    import refit_experiment as R
+    f32 = np.float32
+    P = rows[:, :3].astype(f32).reshape(-1, 3, 3)
+    T = P.shape[0]
+    ext = f32((P.reshape(-1, 3).max(0) - P.reshape(-1, 3).min(0)).max())
+    pad = f32(ext * f32(7.62939453125e-6))
+    lo, hi = (P.min(1) - pad).astype(f32), (P.max(1) + pad).astype(f32)
+    slo, shi = lo.min(0), hi.max(0)
+    cen = ((lo.astype(np.float64) + hi) * 0.5 - slo) / float((shi - slo).max())
+    order = np.argsort(R.morton30(cen), kind="stable")
+    children, clo, chi, root = R.ploc(lo[order].astype(np.float64), hi[order].astype(np.float64))
+    n_inner = T - 1
+    assert root == n_inner - 1
+    remap = lambda ref: np.where(ref >= 0, n_inner - 1 - ref, ref)
+    nodes = np.zeros((n_inner, 16), f32)
+    new = n_inner - 1 - np.arange(n_inner)
+    nodes[new, 0], nodes[new, 1], nodes[new, 2], nodes[new, 3] = clo[:, 0, 0], chi[:, 0, 0], clo[:, 0, 1], chi[:, 0, 1]
+    nodes[new, 4], nodes[new, 5], nodes[new, 6], nodes[new, 7] = clo[:, 1, 0], chi[:, 1, 0], clo[:, 1, 1], chi[:, 1, 1]
+    nodes[new, 8], nodes[new, 9], nodes[new, 10], nodes[new, 11] = clo[:, 0, 2], chi[:, 0, 2], clo[:, 1, 2], chi[:, 1, 2]
+    ni = nodes.view(np.int32)
+    ni[new, 12], ni[new, 13] = remap(children[:, 0]), remap(children[:, 1])
+    tris = np.zeros((T, 12), f32)
+    tris[:, 0:3] = P[order, 0]
+    tris.view(np.uint32)[:, 3] = order.astype(np.uint32)
+    tris[:, 4:7] = P[order, 1] - P[order, 0]
+    tris[:, 8:11] = P[order, 2] - P[order, 0]
+    return nodes, tris
+
+
+def main(n_tris=1500, W=96, H=64):
+    import build as emu_build
+    import oracle
+    import rendering as ren
+    from rendering._raycaster import camera_frame
+    from rendertoy_b200 import scenes
+    oracle.build()
+    L = C.CDLL(emu_build.build("rt_raycast"))
+    VP, I64, I32, FP = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_float)
+    L.rt_raycast_primary.argtypes = [VP, VP, I64, VP, VP, VP, FP, I32, I32, I32, I32, I32, I32, I32, C.c_uint64, VP, VP, I64, VP,
+                                     C.POINTER(C.c_int), I32, VP, VP]
+    L.rt_raycast_view_node_bytes.restype = I64
+    L.rt_raycast_view_node_bytes.argtypes = [I64]
+    L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
+    L.rt_last_error.restype = C.c_char_p
+
+    rows = scenes.dragon(n_tris)
+    T = rows.shape[0] // 3
+    nodes, tris = library_bvh(rows)
+    pos4 = np.ones((3 * T, 4), np.float32); pos4[:, :3] = rows[:, 0:3]
+    nrm4 = np.zeros((3 * T, 4), np.float32); nrm4[:, :3] = rows[:, 4:7]
+    vnodes = np.zeros(int(L.rt_raycast_view_node_bytes(T)), np.uint8)
+    ok = True
+    for lesson, t in ((6, 0.5), (8, 2.2)):
+        world, view, proj = scenes.lesson_camera(ren, lesson, t, W, H)
+        cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+        ref_t, ref_id, ref_u, ref_v = oracle.raycast_brute(rows, oracle.primary_rays(cam, W, H))
+        ref_px = oracle.shade_hits(8, rows, ref_id, ref_u, ref_v).reshape(H, W, 4)
+        cull = (C.c_int * 4)()
+        lo, hi = rows[:, 0:3].min(0).astype(np.float64), rows[:, 0:3].max(0).astype(np.float64)
+        L.rt_raycast_screen_bounds.argtypes = [FP, C.POINTER(C.c_double), C.POINTER(C.c_double), I32, I32, C.POINTER(C.c_int)]
+        has_cull = L.rt_raycast_screen_bounds(cam.ctypes.data_as(FP), lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)), W, H, cull)
+        variants = [("3-D per-lane walk", 0, 0.0, False), ("screen-space packets (measured path)", 0, 0.0, True)]
+        variants += [(f"refit x{k}", k, 0.0, True) for k in (1, 4, 16)]
+        variants += [(f"region traversal a_max={a:g}, refit x{k}", k, a, True) for a, k in ((8.0, 0), (2.0, 0), (64.0, 4), (8.0, 16), (0.001, 0))]
+        for label, passes, a_max, use_view in variants:
+            assert L.rt_raycast_set_view_refit(passes) == 0 and L.rt_raycast_set_region_traversal(a_max) == 0
+            hits = np.full((W * H, 4), np.nan, np.float32)
+            bgra = np.full((H, W), 0x55555555, np.uint32)
+            stats = np.zeros(3, np.uint64)
+            t0 = time.time()
+            rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
+                                      W, H, 0, 0, W, H, 8, 0, hits.ctypes.data, bgra.ctypes.data, W, stats.ctypes.data,
+                                      cull if has_cull else None, 0, vnodes.ctypes.data if use_view else None, None)
+            assert rc == 0, L.rt_last_error()
+            same = (np.array_equal(hits[:, 0].view(np.uint32), ref_t.view(np.uint32)) and np.array_equal(hits[:, 1].view(np.uint32), ref_id)
+                    and np.array_equal(hits[:, 2].view(np.uint32), ref_u.view(np.uint32)) and np.array_equal(hits[:, 3].view(np.uint32), ref_v.view(np.uint32)))
+            same_px = np.array_equal(bgra.view(np.uint8).reshape(H, W, 4), ref_px)
+            ok &= same and same_px
+            rays = max(int(stats[2]), 1)
+            print(f"lesson{lesson:02d} {W}x{H} T={T}  {label:42s} hits {'==' if same else '!='} oracle, pixels {'==' if same_px else '!='}; "
+                  f"{int(stats[0]) / rays:5.1f} node visits, {int(stats[1]) / rays:4.2f} triangle tests per ray ({time.time() - t0:.1f} s)", flush=True)
+    L.rt_raycast_set_view_refit(0); L.rt_raycast_set_region_traversal(0.0)
+    print("ALL BIT-EXACT" if ok else "MISMATCH")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    a = [int(x) for x in sys.argv[1:]]
+    sys.exit(main(*(a[:1] or [1500]), *(a[1:3] if len(a) >= 3 else (96, 64))))

@@ -675,22 +675,26 @@ __global__ void __launch_bounds__(TB, 8) raycast_region_kernel(const TraceArgs a
                 const float4 rc = f_rect[e];
                 cand = rc.x <= tsx_hi && rc.y >= tsx_lo && rc.z <= tsy_hi && rc.w >= tsy_lo;
             }
-            unsigned zkey = cand ? __float_as_uint(f_zi[e].x) : 0xffffffffu; // depth bounds are >= 0: their bits order like their values
+            // depth bounds are >= 0, so their bits order like their values; the low five bits carry the lane, which makes the
+            // warp minimum name its owner (the order among bounds that differ only there does not matter: it is only an order)
+            unsigned zkey = cand ? ((__float_as_uint(f_zi[e].x) & ~31u) | (unsigned)lane) : 0xffffffffu;
             unsigned cmask = __ballot_sync(FULL, cand);
             while (cmask != 0u) {
                 const unsigned znear = __reduce_min_sync(FULL, zkey);
-                const int src = __ffs(__ballot_sync(FULL, cand && zkey == znear)) - 1;
-                if (src < 0) break; // cannot happen: cmask names at least one candidate and the minimum is one of them
-                if (lane == src) { cand = false; zkey = 0xffffffffu; }
+                if (znear == 0xffffffffu) break; // cannot happen while cmask names a candidate (a bound never has all bits set)
+                const int src = (int)(znear & 31u);
+                if (lane == src) zkey = 0xffffffffu;
                 cmask &= ~(1u << src);
                 const float4 rc = f_rect[base + src];
                 const float2 zi = f_zi[base + src];
                 const bool near_enough = live && zi.x <= tbest;
-                if (__ballot_sync(FULL, near_enough) == 0u) break; // nearest first: nothing later in this round can be entered either
                 const unsigned voters = __ballot_sync(FULL, near_enough && sx >= rc.x && sx <= rc.y && sy >= rc.z && sy <= rc.w);
-                if (voters != 0u)
+                if (voters != 0u) {
                     walk_view_packet<STATS>(a, __float_as_int(zi.y), voters, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstack, best, tbest,
                                             bu, bv, n_nodes, n_tests);
+                } else if (__ballot_sync(FULL, live && __uint_as_float(znear & ~31u) <= tbest) == 0u) {
+                    break; // keys ascend and a key's float (low bits cleared) is <= its bound: nothing later in this round can be entered
+                }
             }
         }
         if (STATS && live) {

@@ -54,6 +54,16 @@ def library_bvh(rows):
     return nodes, tris
 
 
+def rays_traced_tiles(cull, W, H):
+    """number of 8x4 tiles the kernels trace (those touching the cull rect)"""
+    if cull is None:
+        return ((W + 7) // 8) * ((H + 3) // 4)
+    x0, y0, x1, y1 = max(cull[0], 0), max(cull[1], 0), min(cull[2], W - 1), min(cull[3], H - 1)
+    if x1 < x0 or y1 < y0:
+        return 0
+    return ((x1 >> 3) - (x0 >> 3) + 1) * ((y1 >> 2) - (y0 >> 2) + 1)
+
+
 def main(n_tris=1500, W=96, H=64):
     import build as emu_build
     import oracle
@@ -69,6 +79,7 @@ def main(n_tris=1500, W=96, H=64):
     L.rt_raycast_view_node_bytes.argtypes = [I64]
     L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
     L.rt_last_error.restype = C.c_char_p
+    counts = (C.c_ulonglong * 5)()
 
     rows = scenes.dragon(n_tris)
     T = rows.shape[0] // 3
@@ -95,17 +106,21 @@ def main(n_tris=1500, W=96, H=64):
             bgra = np.full((H, W), 0x55555555, np.uint32)
             stats = np.zeros(3, np.uint64)
             t0 = time.time()
+            L.emu_counts_read(counts, 1)
             rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
                                       W, H, 0, 0, W, H, 8, 0, hits.ctypes.data, bgra.ctypes.data, W, stats.ctypes.data,
                                       cull if has_cull else None, 0, vnodes.ctypes.data if use_view else None, None)
             assert rc == 0, L.rt_last_error()
+            L.emu_counts_read(counts, 1)
+            tiles = max(rays_traced_tiles(cull if has_cull else None, W, H), 1)
             same = (np.array_equal(hits[:, 0].view(np.uint32), ref_t.view(np.uint32)) and np.array_equal(hits[:, 1].view(np.uint32), ref_id)
                     and np.array_equal(hits[:, 2].view(np.uint32), ref_u.view(np.uint32)) and np.array_equal(hits[:, 3].view(np.uint32), ref_v.view(np.uint32)))
             same_px = np.array_equal(bgra.view(np.uint8).reshape(H, W, 4), ref_px)
             ok &= same and same_px
             rays = max(int(stats[2]), 1)
             print(f"lesson{lesson:02d} {W}x{H} T={T}  {label:42s} hits {'==' if same else '!='} oracle, pixels {'==' if same_px else '!='}; "
-                  f"{int(stats[0]) / rays:5.1f} node visits, {int(stats[1]) / rays:4.2f} triangle tests per ray ({time.time() - t0:.1f} s)", flush=True)
+                  f"{int(stats[0]) / rays:5.1f} node visits, {int(stats[1]) / rays:4.2f} triangle tests per ray; per traced tile: "
+                  f"{counts[0] / tiles:6.1f} votes, {counts[1] / tiles:4.1f} warp-min, {counts[3] / 32 / tiles:6.1f} wide loads ({time.time() - t0:.1f} s)", flush=True)
     L.rt_raycast_set_view_refit(0); L.rt_raycast_set_region_traversal(0.0)
     print("ALL BIT-EXACT" if ok else "MISMATCH")
     return 0 if ok else 1

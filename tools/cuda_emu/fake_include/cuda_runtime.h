@@ -49,8 +49,9 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <typename T> inline T tex1Dfetch(cudaTextureObject_t tex, int i) { return reinterpret_cast<const T *>((uintptr_t)tex)[i]; }
 
-template <typename T> inline T __ldg(const T *p) { return *p; }
-template <typename T> inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p) , *p; }
+inline thread_local unsigned long long t_emu_loads = 0;     // per-thread __ldg / __ldcg calls, summed into warp_loads / 32 at exit
+template <typename T> inline T __ldg(const T *p) { ++t_emu_loads; return *p; }
+template <typename T> inline T __ldcg(const T *p) { ++t_emu_loads; return *p; }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
@@ -68,6 +69,17 @@ inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_S
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
+// warp-level event counters (one count per warp, not per lane): a hardware-independent proxy for how much a kernel variant
+// executes -- a node visit of the packet walk is 3 wide loads + 2 votes, a pop 1 vote, a leaf visit 3 wide loads
+struct EmuCounts { std::atomic<unsigned long long> votes{0}, reduces{0}, shuffles{0}, warp_loads{0}, block_syncs{0}; };
+inline EmuCounts g_emu_counts;
+extern "C" __attribute__((used, visibility("default"))) void emu_counts_read(unsigned long long *out5, int reset)
+{
+    out5[0] = g_emu_counts.votes; out5[1] = g_emu_counts.reduces; out5[2] = g_emu_counts.shuffles; out5[3] = g_emu_counts.warp_loads;
+    out5[4] = g_emu_counts.block_syncs;
+    if (reset) { g_emu_counts.votes = 0; g_emu_counts.reduces = 0; g_emu_counts.shuffles = 0; g_emu_counts.warp_loads = 0; g_emu_counts.block_syncs = 0; }
+}
+
 // ---- block / warp state of the block that is currently running ------------------------------------------------------
 struct EmuWarp {
     std::barrier<> bar{32};
@@ -81,7 +93,11 @@ struct EmuBlock {
 inline EmuBlock *g_emu_block = nullptr;
 inline EmuWarp &emu_warp() { return *g_emu_block->warps[threadIdx.x >> 5]; }
 
-inline void __syncthreads() { g_emu_block->bar->arrive_and_wait(); }
+inline void __syncthreads()
+{
+    if (threadIdx.x == 0) ++g_emu_counts.block_syncs;
+    g_emu_block->bar->arrive_and_wait();
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.arrive_and_wait(); }
 
 // every collective: publish, barrier, read all live lanes, barrier (so nobody overwrites a slot somebody still reads)
@@ -96,6 +112,7 @@ template <typename F> inline auto emu_collective(unsigned long long mine, F comb
 }
 inline unsigned __ballot_sync(unsigned, bool pred)
 {
+    if ((threadIdx.x & 31) == 0) ++g_emu_counts.votes;
     return emu_collective(pred ? 1ull : 0ull, [](const unsigned long long *s, unsigned alive) {
         unsigned m = 0;
         for (int i = 0; i < 32; ++i)
@@ -105,10 +122,12 @@ inline unsigned __ballot_sync(unsigned, bool pred)
 }
 inline int __shfl_sync(unsigned, int v, int src)
 {
+    if ((threadIdx.x & 31) == 0) ++g_emu_counts.shuffles;
     return emu_collective((unsigned long long)(unsigned)v, [src](const unsigned long long *s, unsigned) { return (int)(unsigned)s[src & 31]; });
 }
 inline unsigned __reduce_min_sync(unsigned, unsigned v)
 {
+    if ((threadIdx.x & 31) == 0) ++g_emu_counts.reduces;
     return emu_collective((unsigned long long)v, [](const unsigned long long *s, unsigned alive) {
         unsigned m = 0xffffffffu;
         for (int i = 0; i < 32; ++i)
@@ -131,7 +150,9 @@ template <typename F> inline void emu_launch(unsigned grid, unsigned block, F bo
         for (unsigned t = 0; t < block; ++t)
             threads.emplace_back([&, t] {
                 threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                t_emu_loads = 0;
                 body();
+                g_emu_counts.warp_loads += t_emu_loads;  // thread-level; readers divide by 32 for a warp-level lower bound
                 EmuWarp &w = *blk.warps[t >> 5];          // an exited thread no longer takes part in anything
                 w.alive.fetch_and(~(1u << (t & 31)));
                 w.bar.arrive_and_drop();

@@ -641,6 +641,10 @@ def main():
                     help="--gather copy: push whole frames instead of the rect that can differ from the clear colour")
     ap.add_argument("--dense-readback", dest="sparse_readback", action="store_false",
                     help="e2e: read whole ray-cast frames back instead of the rect that can differ from the clear colour")
+    ap.add_argument("--view-refit", type=int, default=0, help="EXPERIMENTAL, unmeasured: tightening passes over the screen-space nodes "
+                    "(rt_raycast_set_view_refit); 0 = the measured path")
+    ap.add_argument("--region-amax", type=float, default=0.0, help="EXPERIMENTAL, unmeasured: two-level region traversal with this frontier "
+                    "threshold in tiles (rt_raycast_set_region_traversal); 0 = the measured path")
     ap.add_argument("--gather", default="copy", choices=["peer", "copy", "nccl"],
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
                          "IPC-mapped frame store while the next frame traces (default: fastest from N=4 up); peer = the kernels store "
@@ -660,7 +664,13 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     rank, world, local = dist_setup(args.gpus)
+    if args.view_refit or args.region_amax:
+        from rendertoy_b200 import _native
+        _native.call("rt_raycast_set_view_refit", args.view_refit)
+        _native.call("rt_raycast_set_region_traversal", args.region_amax)
     ray, rows = bench_raycast(args, rank, world)
+    if args.view_refit or args.region_amax:
+        ray["config"]["experimental"] = {"view_refit_passes": args.view_refit, "region_amax_tiles": args.region_amax}
     ras = bench_raster(args, rank, world, rows)
     if rank == 0:
         if not args.no_cpu_baseline:

@@ -395,7 +395,7 @@ def bench_raycast(args, rank, world):
                                         "of the scene's projected bounds of this frame and of the frame the host buffer held before); the host "
                                         "frame is complete and checked against the device frame after the timed region" if args.sparse_readback
                                         else " of the whole 33 MB frame") + "; every rank reads back its own frames"},
-        "gpu_launches": 2 * F * args.steps, "clocks": clocks,   # project_kernel + raycast_kernel per frame
+        "gpu_launches": (2 + args.view_refit) * F * args.steps, "clocks": clocks,   # project_kernel (+ experimental refit passes) + raycast kernel per frame
     }
     return out, rows
 

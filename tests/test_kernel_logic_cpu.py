@@ -15,3 +15,11 @@ def test_raycast_kernels_on_the_cpu_emulator():
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raycast
     assert check_raycast.main(600, 64, 32) == 0
+
+
+@pytest.mark.timeout(600)
+def test_raycast_kernel_edge_cases_on_the_cpu_emulator():
+    """camera inside the mesh (unbounded rectangles), single-triangle scene, sub-rectangle with a pitch, no cull rectangle"""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+    import check_raycast
+    assert check_raycast.edges() == 0

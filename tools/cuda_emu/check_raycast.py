@@ -126,6 +126,75 @@ def main(n_tris=1500, W=96, H=64):
     return 0 if ok else 1
 
 
+def edges():
+    """Edge cases through every variant: the camera inside the mesh (unbounded rectangles: the region walk cannot stop early
+    and must fall back), a single-triangle scene (the one-node tree with an empty second child), a sub-rectangle of the frame
+    with a pitch, and no cull rectangle."""
+    import build as emu_build
+    import oracle
+    from rendertoy_b200 import scenes
+    oracle.build()
+    L = C.CDLL(emu_build.build("rt_raycast"))
+    VP, I64, I32, FP = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_float)
+    L.rt_raycast_primary.argtypes = [VP, VP, I64, VP, VP, VP, FP, I32, I32, I32, I32, I32, I32, I32, C.c_uint64, VP, VP, I64, VP,
+                                     C.POINTER(C.c_int), I32, VP, VP]
+    L.rt_raycast_view_node_bytes.restype = I64
+    L.rt_raycast_view_node_bytes.argtypes = [I64]
+    L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
+    L.rt_last_error.restype = C.c_char_p
+    W, H = 72, 44
+    ok = True
+    rows_big = scenes.dragon(900)
+    one = rows_big[:3].copy()
+    one[:, 0:3] = np.float32([[-0.3, -0.2, 0.1], [0.35, -0.25, 0.0], [0.05, 0.3, -0.1]])
+    inside = np.array([0, 0, 0, 0.8, 0, 0, 0, 0.6, 0, 0, 0, 1], np.float32)
+    outside = np.array([0.1, 0.2, -2.0, 0.5, 0.05, 0, 0, 0.4, 0.02, 0.03, -0.05, 1], np.float32)
+    cases = [("camera inside the mesh", rows_big, inside, (0, 0, W, H)), ("single triangle", one, outside, (0, 0, W, H)),
+             ("sub-rectangle of the frame", rows_big, outside, (8, 4, W - 19, H - 9)), ("dragon from outside, no cull rect", rows_big, outside, (0, 0, W, H))]
+    for name, rows, cam, (x0, y0, w, h) in cases:
+        T = rows.shape[0] // 3
+        if T == 1:                                        # rt_bvh.cu: single_leaf_root_kernel
+            f32 = np.float32
+            P = rows[:, :3].astype(f32)
+            pad = f32((P.max(0) - P.min(0)).max() * f32(7.62939453125e-6))
+            lo, hi = P.min(0) - pad, P.max(0) + pad
+            nodes = np.zeros((1, 16), f32)
+            nodes[0, 0:4] = (lo[0], hi[0], lo[1], hi[1]); nodes[0, 4:8] = (np.inf, -np.inf, np.inf, -np.inf)
+            nodes[0, 8:12] = (lo[2], hi[2], np.inf, -np.inf)
+            nodes.view(np.int32)[0, 12:14] = (~0, ~0)
+            tris = np.zeros((1, 12), f32)
+            tris[0, 0:3] = P[0]; tris[0, 4:7] = P[1] - P[0]; tris[0, 8:11] = P[2] - P[0]
+        else:
+            nodes, tris = library_bvh(rows)
+        pos4 = np.ones((3 * T, 4), np.float32); pos4[:, :3] = rows[:, 0:3]
+        nrm4 = np.zeros((3 * T, 4), np.float32); nrm4[:, :3] = rows[:, 4:7]
+        vnodes = np.zeros(int(L.rt_raycast_view_node_bytes(T)), np.uint8)
+        rr = oracle.primary_rays(cam, W, H, rect=(x0, y0, w, h))
+        ref_t, ref_id, ref_u, ref_v = oracle.raycast_brute(rows, rr)
+        ref_px = oracle.shade_hits(8, rows, ref_id, ref_u, ref_v).reshape(h, w, 4)
+        for label, passes, a_max, use_view in [("3-D", 0, 0.0, False), ("packets", 0, 0.0, True), ("refit x3", 3, 0.0, True),
+                                               ("region 8", 0, 8.0, True), ("region 8 + refit x3", 3, 8.0, True), ("region 0.5", 0, 0.5, True)]:
+            L.rt_raycast_set_view_refit(passes); L.rt_raycast_set_region_traversal(a_max)
+            hits = np.full((w * h, 4), np.nan, np.float32)
+            frame = np.full((H, W), 0x55555555, np.uint32)
+            rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
+                                      W, H, x0, y0, w, h, 8, 0, hits.ctypes.data, frame.ctypes.data + 4 * (y0 * W + x0), W, None, None, 0,
+                                      vnodes.ctypes.data if use_view else None, None)
+            assert rc == 0, L.rt_last_error()
+            same = (np.array_equal(hits[:, 0].view(np.uint32), ref_t.view(np.uint32)) and np.array_equal(hits[:, 1].view(np.uint32), ref_id)
+                    and np.array_equal(hits[:, 2].view(np.uint32), ref_u.view(np.uint32)) and np.array_equal(hits[:, 3].view(np.uint32), ref_v.view(np.uint32)))
+            got_px = frame[y0:y0 + h, x0:x0 + w].copy().view(np.uint8).reshape(h, w, 4)
+            untouched = frame.copy(); untouched[y0:y0 + h, x0:x0 + w] = 0x55555555
+            same_px = np.array_equal(got_px, ref_px) and bool((untouched == 0x55555555).all())
+            ok &= same and same_px
+            print(f"{name:34s} {label:22s} hits {'==' if same else '!='} oracle, pixels {'==' if same_px else '!='} ({int((ref_id != 0xFFFFFFFF).sum())} of {w * h} rays hit)", flush=True)
+    L.rt_raycast_set_view_refit(0); L.rt_raycast_set_region_traversal(0.0)
+    print("EDGE CASES BIT-EXACT" if ok else "EDGE CASE MISMATCH")
+    return 0 if ok else 1
+
+
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["edges"]:
+        sys.exit(edges())
     a = [int(x) for x in sys.argv[1:]]
     sys.exit(main(*(a[:1] or [1500]), *(a[1:3] if len(a) >= 3 else (96, 64))))

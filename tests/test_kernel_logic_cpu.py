@@ -23,3 +23,11 @@ def test_raycast_kernel_edge_cases_on_the_cpu_emulator():
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raycast
     assert check_raycast.edges() == 0
+
+
+@pytest.mark.timeout(600)
+def test_raster_kernels_on_the_cpu_emulator():
+    """raster_kernel / coverage_kernel / resolve_kernel / points, lesson08 + lesson09, clipping camera, composing draws"""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+    import check_raster
+    assert check_raster.main(900, 80, 48) == 0

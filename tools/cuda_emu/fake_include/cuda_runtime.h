@@ -33,13 +33,24 @@ struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) float3 { float x, y, z; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return {x, y}; }
+inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
 inline float2 make_float2(float x, float y) { return {x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 inline int2 make_int2(int x, int y) { return {x, y}; }
 inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
 
-struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
+struct dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    dim3() = default;
+    dim3(unsigned x_, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+    dim3(int x_, int y_ = 1, int z_ = 1) : x((unsigned)x_), y((unsigned)y_), z((unsigned)z_) {}
+};
+typedef dim3 EmuDim3;
 inline thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 
 typedef void *cudaStream_t;
@@ -47,7 +58,19 @@ typedef unsigned long long cudaTextureObject_t;
 enum cudaError_t { cudaSuccess = 0 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+// linear-memory, point-sampled texture objects only: the "object" is the texel pointer
 template <typename T> inline T tex1Dfetch(cudaTextureObject_t tex, int i) { return reinterpret_cast<const T *>((uintptr_t)tex)[i]; }
+enum { cudaResourceTypeLinear = 2, cudaFilterModePoint = 0, cudaReadModeElementType = 0 };
+struct cudaChannelFormatDesc { int x, y, z, w, f; };
+template <typename T> inline cudaChannelFormatDesc cudaCreateChannelDesc() { return {(int)sizeof(T) * 2, 0, 0, 0, 0}; }
+struct cudaResourceDesc { int resType; struct { struct { void *devPtr; cudaChannelFormatDesc desc; size_t sizeInBytes; } linear; } res; };
+struct cudaTextureDesc { int filterMode, readMode, normalizedCoords; };
+inline cudaError_t cudaCreateTextureObject(cudaTextureObject_t *obj, const cudaResourceDesc *rd, const cudaTextureDesc *, const void *)
+{
+    *obj = (cudaTextureObject_t)(uintptr_t)rd->res.linear.devPtr;
+    return cudaSuccess;
+}
+inline cudaError_t cudaDestroyTextureObject(cudaTextureObject_t) { return cudaSuccess; }
 
 inline thread_local unsigned long long t_emu_loads = 0;     // per-thread __ldg / __ldcg calls, summed into warp_loads / 32 at exit
 template <typename T> inline T __ldg(const T *p) { ++t_emu_loads; return *p; }
@@ -57,6 +80,12 @@ inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 inline int __float2int_rn(float f) { return (int)nearbyintf(f); }
+inline int __float2int_ru(float f) { return (int)ceilf(f); }
+inline int __float2int_rd(float f) { return (int)floorf(f); }
+inline float __frcp_rn(float f) { return 1.0f / f; }
+template <typename T> inline T __ldcs(const T *p) { return *p; }
+inline int atomicSub(int *p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicSub(unsigned *p, unsigned v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -65,6 +94,30 @@ inline int max(int a, int b) { return a > b ? a : b; }
 inline long long min(long long a, long long b) { return a < b ? a : b; }
 inline long long max(long long a, long long b) { return a > b ? a : b; }
 
+inline float __fdividef(float a, float b) { return a / b; }     // the GPU's is approximate: callers must not depend on its rounding
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{   // position of the offset-th set bit of mask at or above base (offset > 0), 0xffffffff if there is none
+    int seen = 0;
+    if (offset > 0) { for (unsigned i = base; i < 32; ++i) if ((mask >> i) & 1u) { if (++seen == offset) return i; } }
+    else if (offset < 0) { for (int i = (int)base; i >= 0; --i) if ((mask >> i) & 1u) { if (++seen == -offset) return (unsigned)i; } }
+    else if ((mask >> base) & 1u) return base;
+    return 0xffffffffu;
+}
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned atomicMin(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -125,6 +178,26 @@ inline int __shfl_sync(unsigned, int v, int src)
     if ((threadIdx.x & 31) == 0) ++g_emu_counts.shuffles;
     return emu_collective((unsigned long long)(unsigned)v, [src](const unsigned long long *s, unsigned) { return (int)(unsigned)s[src & 31]; });
 }
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, !pred) == 0u; }
+inline int __shfl_up_sync(unsigned, int v, unsigned delta)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) ++g_emu_counts.shuffles;
+    return emu_collective((unsigned long long)(unsigned)v, [lane, delta](const unsigned long long *s, unsigned) {
+        return (int)(unsigned)s[lane >= (int)delta ? lane - (int)delta : lane];
+    });
+}
+inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    if ((threadIdx.x & 31) == 0) ++g_emu_counts.reduces;
+    return emu_collective((unsigned long long)v, [](const unsigned long long *s, unsigned alive) {
+        unsigned m = 0;
+        for (int i = 0; i < 32; ++i)
+            if ((alive >> i) & 1u) m |= (unsigned)s[i];
+        return m;
+    });
+}
 inline unsigned __reduce_min_sync(unsigned, unsigned v)
 {
     if ((threadIdx.x & 31) == 0) ++g_emu_counts.reduces;
@@ -137,9 +210,10 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v)
 }
 
 // kernel<<<grid, block>>>(args)  ->  emu_launch(grid, block, [&] { kernel(args); })
-template <typename F> inline void emu_launch(unsigned grid, unsigned block, F body)
+template <typename F> inline void emu_launch(dim3 grid3, dim3 block3, F body)
 {
-    if (block % 32 != 0) { fprintf(stderr, "cuda_emu: block size must be a multiple of 32\n"); abort(); }
+    const unsigned grid = grid3.x * grid3.y * grid3.z, block = block3.x;
+    if (block % 32 != 0 || block3.y != 1 || block3.z != 1) { fprintf(stderr, "cuda_emu: 1-D blocks, a multiple of 32 threads\n"); abort(); }
     for (unsigned b = 0; b < grid; ++b) {
         EmuBlock blk;
         blk.bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block);
@@ -149,7 +223,8 @@ template <typename F> inline void emu_launch(unsigned grid, unsigned block, F bo
         threads.reserve(block);
         for (unsigned t = 0; t < block; ++t)
             threads.emplace_back([&, t] {
-                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                threadIdx.x = t; blockDim.x = block; gridDim = grid3;
+                blockIdx.x = b % grid3.x; blockIdx.y = (b / grid3.x) % grid3.y; blockIdx.z = b / (grid3.x * grid3.y);
                 t_emu_loads = 0;
                 body();
                 g_emu_counts.warp_loads += t_emu_loads;  // thread-level; readers divide by 32 for a warp-level lower bound

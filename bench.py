@@ -419,16 +419,25 @@ def bench_raster(args, rank, world, rows=None):
     my_frames = parallel.frame_indices(n_frames, rank, world)
     # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
     store = parallel.FrameStore(2 * n_frames, RAS_W, RAS_H) if (world > 1 and args.gather != "nccl") else None
-    fused = store is not None and store.ok
+    # --raster-gather copy (EXPERIMENTAL, not yet measured): as for the ray-cast frames, ranks != 0 render locally and a copy engine
+    # pushes Raster.content_rect into rank 0's frame store; rank 0 renders in place.  Default: every rank's kernels store into the store.
+    ras_push = store is not None and store.ok and args.raster_gather == "copy"
+    fused = store is not None and store.ok and not ras_push
+    in_store = fused or (ras_push and rank == 0)         # this rank's render targets are slots of the store
     rasters, rasters_b = [], []
     for j in range(F):
-        target = ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(my_frames[j])) if fused else \
+        target = ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(my_frames[j])) if in_store else \
             ren.create_presenter(RAS_W, RAS_H).get_render_target()
         rasters.append(lessons.build_lesson08(ren, target))
-        if fused:   # second half of the double-buffered frame store
+        if in_store:   # second half of the double-buffered frame store
             rasters_b.append(lessons.build_lesson08(ren, ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(n_frames + my_frames[j]))))
-    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (world > 1 and not fused) else None
-    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1 and not fused) else None
+    if ras_push:
+        push_stream = torch.cuda.Stream()
+        push_ptr = push_stream.cuda_stream
+        drawn = [torch.cuda.Event() for _ in range(F)]
+    nccl_gather = world > 1 and not fused and not ras_push
+    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if nccl_gather else None
+    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and nccl_gather) else None
     cams = {k: scenes.lesson_camera(ren, 8, orbit_t(k), RAS_W, RAS_H) for k in range(n_frames * (args.steps + args.warmup + 6))}
 
     # frames of an animation batch are independent: each of the F targets gets its own CUDA stream, so the short
@@ -437,15 +446,17 @@ def bench_raster(args, rank, world, rows=None):
     main_stream = torch.cuda.current_stream()
 
     def frame(j, k, odd=False):
-        raster, g = rasters_b[j] if (odd and fused) else rasters[j]
-        if streams is None:
-            lessons.set_transforms(ren, g, *cams[k])
-            lessons.render_frame(ren, raster, vb)
-            return
-        torch.cuda.set_stream(streams[j])          # (the `with torch.cuda.stream()` context costs ~15 us of Python)
+        raster, g = rasters_b[j] if (odd and in_store) else rasters[j]
+        if streams is not None:
+            torch.cuda.set_stream(streams[j])          # (the `with torch.cuda.stream()` context costs ~15 us of Python)
         lessons.set_transforms(ren, g, *cams[k])
         lessons.render_frame(ren, raster, vb)
-        torch.cuda.set_stream(main_stream)
+        if ras_push and rank != 0:
+            drawn[j].record()
+            push_stream.wait_event(drawn[j])
+            store.push((n_frames if odd else 0) + my_frames[j], raster.get_render_target().ptr, raster.content_rect, push_ptr)
+        if streams is not None:
+            torch.cuda.set_stream(main_stream)
 
     def fork():
         if streams is not None:
@@ -456,9 +467,11 @@ def bench_raster(args, rank, world, rows=None):
         if streams is not None:
             for st in streams:
                 main_stream.wait_stream(st)
+        if ras_push:
+            main_stream.wait_stream(push_stream)
 
     def gather():
-        if fused:
+        if fused or ras_push:
             store.commit()
         elif world > 1:
             for j in range(F):
@@ -481,6 +494,16 @@ def bench_raster(args, rank, world, rows=None):
         step(args.warmup + s)
     e1.record()
     barrier_sync(world)
+    if ras_push:   # untimed check, as for the ray-cast frames: the slots of the last step hold exactly what this rank rendered
+        odd_last = bool((args.warmup + args.steps - 1) & 1)
+        okf = 1
+        if rank != 0:
+            for j in range(F):
+                slot = store.frame((n_frames if odd_last else 0) + my_frames[j]).view(torch.int32)
+                okf &= int(torch.equal(slot, rasters[j][0].get_render_target().buffer.tensor().view(torch.int32).view(-1)))
+        flag = torch.tensor([okf], dtype=torch.int32, device="cuda")
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        assert bool(flag.item()), "raster frames in rank 0's frame store differ from the frames the ranks rendered"
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     tris_total = N_TRIS * n_frames * args.steps
     value = tris_total / (ms * 1e-3) / 1e6
@@ -531,7 +554,8 @@ def bench_raster(args, rank, world, rows=None):
         "metric": METRIC_RAS, "value": value, "unit": "Mtris/s", "ms_per_step": ms / args.steps,
         "config": {"workload": "configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders, clear + clear + draw_triangles per frame",
                    "frames_per_rank_per_step": F, "l2": "8 independent raster targets per rank (~300 MB of key/colour/record buffers > L2)",
-                   "streams": "one CUDA stream per frame target (frames of a batch are independent)" if streams else "single stream"},
+                   "streams": "one CUDA stream per frame target (frames of a batch are independent)" if streams else "single stream",
+                   **({"gather": "EXPERIMENTAL copy-engine push of Raster.content_rect, verified against the local frames"} if ras_push else {})},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": ncu_traffic().get("raster_frame"), "peak_source": peak_src, "unit_of_work": "one frame = 5 kernels "
                      "(2 clears, raster_kernel, coverage_kernel, resolve_kernel); algorithmic bytes are defined per frame",
@@ -645,6 +669,9 @@ def main():
                     "(rt_raycast_set_view_refit); 0 = the measured path")
     ap.add_argument("--region-amax", type=float, default=0.0, help="EXPERIMENTAL, unmeasured: two-level region traversal with this frontier "
                     "threshold in tiles (rt_raycast_set_region_traversal); 0 = the measured path")
+    ap.add_argument("--raster-gather", default="peer", choices=["peer", "copy"],
+                    help="N>1, raster frames: peer = the kernels store into rank 0's frame store (default, measured); copy = EXPERIMENTAL, "
+                         "not yet measured: render locally, push Raster.content_rect with the copy engine")
     ap.add_argument("--gather", default="copy", choices=["peer", "copy", "nccl"],
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
                          "IPC-mapped frame store while the next frame traces (default: fastest from N=4 up); peer = the kernels store "

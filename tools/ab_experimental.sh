@@ -8,10 +8,10 @@ set -x
 mkdir -p gpurun_out
 {
 RENDERTOY_B200_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_raycast_gpu.py -q -k experimental -s 2>&1 | tail -40
-for refit in 0 1 2 4 8; do RT_VIEW_REFIT=$refit timeout 120 python tools/quick_raycast_bench.py ncu 2>&1 | grep -E "refit|render"; done
+for refit in 0 1 2 4 8; do RT_VIEW_REFIT=$refit timeout 120 python tools/quick_raycast_bench.py ab 2>&1 | grep -E "refit|render"; done
 for amax in 2 8 32; do
-  RT_REGION_AMAX=$amax timeout 120 python tools/quick_raycast_bench.py ncu 2>&1 | grep -E "region|render"
-  RT_VIEW_REFIT=4 RT_REGION_AMAX=$amax timeout 120 python tools/quick_raycast_bench.py ncu 2>&1 | grep -E "refit|region|render"
+  RT_REGION_AMAX=$amax timeout 120 python tools/quick_raycast_bench.py ab 2>&1 | grep -E "region|render"
+  RT_VIEW_REFIT=4 RT_REGION_AMAX=$amax timeout 120 python tools/quick_raycast_bench.py ab 2>&1 | grep -E "refit|region|render"
 done
 timeout 200 python bench.py --no-cpu-baseline --view-refit 4 --region-amax 8 2>/dev/null | cut -c1-400
 } > gpurun_out/ab_experimental.log 2>&1

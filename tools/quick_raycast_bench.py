@@ -42,9 +42,10 @@ if __name__ == "__main__":
         from rendertoy_b200 import _native
         _native.call("rt_raycast_set_region_traversal", float(os.environ["RT_REGION_AMAX"]))
         print("region traversal, frontier threshold (tiles):", os.environ["RT_REGION_AMAX"])
-    fr = 3 if len(sys.argv) > 1 and sys.argv[1] == "ncu" else 20
+    mode = sys.argv[1] if len(sys.argv) > 1 else ""
+    fr = 3 if mode == "ncu" else (40 if mode == "ab" else 20)     # ncu: few launches to profile; ab: the two 4K frames only, 40 frames each
     run(100_000, 3840, 2160, 6, fr); sys.stdout.flush()
     run(100_000, 3840, 2160, 8, fr)
-    if fr > 3:
+    if mode == "":
         run(100_000, 1920, 1080, 8, fr)
         run(1_000_000, 3840, 2160, 6, fr)

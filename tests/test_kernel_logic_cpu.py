@@ -31,3 +31,12 @@ def test_raster_kernels_on_the_cpu_emulator():
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raster
     assert check_raster.main(900, 80, 48) == 0
+
+
+@pytest.mark.timeout(600)
+def test_bvh_builders_on_the_cpu_emulator():
+    """bounds / Morton / radix sort / Karras + refit / PLOC rounds: valid trees (soup, indexed, duplicate Morton codes, one
+    triangle), and the emulated traversal over them reproduces the oracle's hits"""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+    import check_bvh
+    assert check_bvh.main(300, 48, 32) == 0

@@ -57,6 +57,9 @@ typedef void *cudaStream_t;
 typedef unsigned long long cudaTextureObject_t;
 enum cudaError_t { cudaSuccess = 0 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t = nullptr) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 // linear-memory, point-sampled texture objects only: the "object" is the texel pointer
 template <typename T> inline T tex1Dfetch(cudaTextureObject_t tex, int i) { return reinterpret_cast<const T *>((uintptr_t)tex)[i]; }
@@ -118,6 +121,26 @@ inline unsigned atomicMin(unsigned *p, unsigned v)
     return old;
 }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline int atomicMin(int *p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline int atomicMax(int *p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned atomicMax(unsigned *p, unsigned v)
+{
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+template <typename T> inline void __stcg(T *p, T v) { *p = v; }
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -135,9 +158,10 @@ extern "C" __attribute__((used, visibility("default"))) void emu_counts_read(uns
 
 // ---- block / warp state of the block that is currently running ------------------------------------------------------
 struct EmuWarp {
-    std::barrier<> bar{32};
+    std::barrier<> bar;
     unsigned long long slot[32];
-    std::atomic<unsigned> alive{0xffffffffu};
+    std::atomic<unsigned> alive;
+    explicit EmuWarp(unsigned lanes) : bar((std::ptrdiff_t)lanes), alive(lanes >= 32 ? 0xffffffffu : ((1u << lanes) - 1u)) {}
 };
 struct EmuBlock {
     std::unique_ptr<std::barrier<>> bar;
@@ -188,6 +212,25 @@ inline int __shfl_up_sync(unsigned, int v, unsigned delta)
         return (int)(unsigned)s[lane >= (int)delta ? lane - (int)delta : lane];
     });
 }
+inline int __shfl_xor_sync(unsigned, int v, int lane_mask)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) ++g_emu_counts.shuffles;
+    return emu_collective((unsigned long long)(unsigned)v, [lane, lane_mask](const unsigned long long *s, unsigned) { return (int)(unsigned)s[(lane ^ lane_mask) & 31]; });
+}
+inline unsigned __shfl_xor_sync(unsigned m, unsigned v, int lane_mask) { return (unsigned)__shfl_xor_sync(m, (int)v, lane_mask); }
+inline float __shfl_xor_sync(unsigned m, float v, int lane_mask) { return __int_as_float(__shfl_xor_sync(m, __float_as_int(v), lane_mask)); }
+inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) ++g_emu_counts.votes;
+    return emu_collective((unsigned long long)v, [lane](const unsigned long long *s, unsigned alive) {
+        unsigned m = 0;
+        for (int i = 0; i < 32; ++i)
+            if (((alive >> i) & 1u) && s[i] == s[lane]) m |= 1u << i;
+        return m;
+    });
+}
 inline unsigned __reduce_or_sync(unsigned, unsigned v)
 {
     if ((threadIdx.x & 31) == 0) ++g_emu_counts.reduces;
@@ -213,11 +256,11 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v)
 template <typename F> inline void emu_launch(dim3 grid3, dim3 block3, F body)
 {
     const unsigned grid = grid3.x * grid3.y * grid3.z, block = block3.x;
-    if (block % 32 != 0 || block3.y != 1 || block3.z != 1) { fprintf(stderr, "cuda_emu: 1-D blocks, a multiple of 32 threads\n"); abort(); }
+    if (block == 0 || block3.y != 1 || block3.z != 1) { fprintf(stderr, "cuda_emu: 1-D blocks only\n"); abort(); }
     for (unsigned b = 0; b < grid; ++b) {
         EmuBlock blk;
         blk.bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block);
-        for (unsigned w = 0; w < block / 32; ++w) blk.warps.push_back(std::make_unique<EmuWarp>());
+        for (unsigned w = 0; w * 32 < block; ++w) blk.warps.push_back(std::make_unique<EmuWarp>(block - w * 32 < 32 ? block - w * 32 : 32u));
         g_emu_block = &blk;
         std::vector<std::thread> threads;
         threads.reserve(block);

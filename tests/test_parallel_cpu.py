@@ -160,3 +160,75 @@ def test_screen_bounds_native_matches_numpy(ren):
     far = np.array([1e6, 0, 3, 1, 0, 0, 0, 1, 0, 0, 0, -1], np.float32)           # scene far off to the side: clamped, maybe empty
     r = rc.screen_bounds(far, 640, 480)
     assert r is None or (0 <= r[0] and r[2] <= 639 and 0 <= r[1] and r[3] <= 479)
+
+
+def _sparse_worker(rank, world, port, shm_name, w, h, F, steps, out):
+    """The bench's sparse-push protocol with the CUDA pieces swapped for host ones: rank 0's double-buffered frame store is a
+    shared-memory block every rank maps (CUDA IPC in the product), rt_copy_rect is the host copy above, commit is a gloo
+    all-reduce.  Frames: k = rank (mod world); slot (s % 2) * n_frames + k; only cover_rect travels."""
+    from multiprocessing import shared_memory
+    from rendertoy_b200 import _native
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    try:
+        _native.call = _fake_copy_rect
+        n_frames = F * world
+        store = np.ndarray((2 * n_frames, h, w), np.uint32, buffer=shm.buf)
+        base = store.ctypes.data
+        copier = parallel.SparseFrameCopier(w, h)
+        mine = parallel.frame_indices(n_frames, rank, world)
+        flag = torch.zeros(1, dtype=torch.int32)
+        ok = True
+
+        def frame(s, k):                                     # what "rendering" frame k of step s produces, on any rank
+            rng = np.random.default_rng(1000 * s + k)
+            f = np.zeros((h, w), np.uint32)
+            x0, x1 = sorted(rng.integers(0, w, 2)); y0, y1 = sorted(rng.integers(0, h, 2))
+            if (s + k) % 7 == 0:
+                return f, (3, 3, 2, 2)                       # nothing visible this frame
+            f[y0:y1 + 1, x0:x1 + 1] = rng.integers(1, 2 ** 32, (y1 - y0 + 1, x1 - x0 + 1), dtype=np.uint32)
+            return f, (int(x0), int(y0), int(x1), int(y1))
+
+        for s in range(steps):
+            for k in mine:
+                f, content = frame(s, k)
+                slot = (s % 2) * n_frames + k
+                if rank == 0:
+                    store[slot] = f                          # rank 0 renders in place (whole frame, clear pixels included)
+                else:
+                    copier.copy(slot, base + slot * w * h * 4, f.ctypes.data, content, None)
+            dist.all_reduce(flag)                            # commit: every rank's pushes of this step are done
+            if rank == 0:
+                for k in range(n_frames):
+                    ok &= bool(np.array_equal(store[(s % 2) * n_frames + k], frame(s, k)[0]))
+            dist.barrier()                                   # (the product re-uses a slot only two commits later)
+        if rank == 0:
+            out.put(ok)
+        else:
+            out.put(copier.bytes_moved < 0.8 * steps * F * w * h * 4)
+    finally:
+        shm.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sparse_push_protocol_world_size_2_gloo():
+    from multiprocessing import shared_memory
+    w, h, F, steps = 96, 40, 3, 6
+    shm = shared_memory.SharedMemory(create=True, size=2 * F * 2 * w * h * 4)
+    try:
+        np.ndarray((2 * F * 2, h, w), np.uint32, buffer=shm.buf)[:] = 0      # the store starts cleared
+        ctx = mp.get_context("spawn")
+        out = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, shm.name, w, h, F, steps, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(100)
+            assert p.exitcode == 0
+        assert out.get(timeout=5) is True and out.get(timeout=5) is True
+    finally:
+        shm.close()
+        shm.unlink()

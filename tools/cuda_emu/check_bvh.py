@@ -55,7 +55,7 @@ def validate_tree(nodes, tris, n, label):
 
 
 def main(n_tris=700, W=64, H=40):
-    import build as emu_build
+    import emu_build
     import oracle
     import rendering as ren
     from rendering._raycaster import camera_frame

@@ -22,7 +22,7 @@ os.environ.setdefault("RENDERTOY_B200_HOST_BUFFERS", "1")
 
 
 def main(n_tris=1200, W=96, H=64):
-    import build as emu_build
+    import emu_build
     import oracle
     from oracle import host_math as hm
     from rendertoy_b200 import scenes

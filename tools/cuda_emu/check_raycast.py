@@ -65,7 +65,7 @@ def rays_traced_tiles(cull, W, H):
 
 
 def main(n_tris=1500, W=96, H=64):
-    import build as emu_build
+    import emu_build
     import oracle
     import rendering as ren
     from rendering._raycaster import camera_frame
@@ -130,7 +130,7 @@ def edges():
     """Edge cases through every variant: the camera inside the mesh (unbounded rectangles: the region walk cannot stop early
     and must fall back), a single-triangle scene (the one-node tree with an empty second child), a sub-rectangle of the frame
     with a pitch, and no cull rectangle."""
-    import build as emu_build
+    import emu_build
     import oracle
     from rendertoy_b200 import scenes
     oracle.build()

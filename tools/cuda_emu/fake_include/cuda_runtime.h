@@ -1,6 +1,6 @@
 // tools/cuda_emu -- DEV-TIME TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 // A just-enough CUDA execution model for the host: lets the SOURCE of a kernel file (csrc/*.cu, launches rewritten by
-// tools/cuda_emu/build.py) run on CPU threads -- one std::thread per CUDA thread, blocks one after the other, __syncthreads and
+// tools/cuda_emu/emu_build.py) run on CPU threads -- one std::thread per CUDA thread, blocks one after the other, __syncthreads and
 // the warp collectives as barriers -- so that kernel LOGIC (indexing, shared-memory protocols, vote / reduce sequences,
 // conservativeness of tests) can be checked against the oracle without a GPU.  It says nothing about performance, memory
 // ordering subtleties or anything the hardware does differently from "32 lanes arriving at every collective".

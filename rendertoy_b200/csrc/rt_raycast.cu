@@ -516,7 +516,13 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
 // If the frontier or a queue overflows, the frontier becomes {root}: phase 2 is then exactly the one-level walk.
 // Hits cannot differ from the one-level walk: both enter a leaf for a lane iff the lane's pixel passes the rectangle and depth
 // tests of a chain of ancestors that all contain the leaf; the exact test at the leaf is the same code.
-constexpr int REG_TX = 8, REG_TY = 4;           // tiles per region
+#ifndef RT_REGION_TX
+#define RT_REGION_TX 8
+#endif
+#ifndef RT_REGION_TY
+#define RT_REGION_TY 4
+#endif
+constexpr int REG_TX = RT_REGION_TX, REG_TY = RT_REGION_TY; // tiles per region (-D overrides for A/B builds)
 constexpr int REG_FCAP = 128, REG_QCAP = 256;   // frontier entries / nodes per breadth-first level
 
 float g_region_a_max_tiles = 0.0f; // rt_raycast_set_region_traversal: 0 = off

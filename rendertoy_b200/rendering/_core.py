@@ -738,34 +738,45 @@ def _r32(x):
 
 
 def _rotate_numpy(angle, axis):
-    """rotate() as first written, on NumPy arrays; kept as the definition the scalar version is tested against."""
-    c, s = np.float64(np.cos(angle)), np.float64(np.sin(angle))
-    ax = to_array(axis)
+    """rotate() on NumPy scalars: the definition the scalar version is tested against.  Row i, column j of the 3x3 block is
+    a_j*a_i*(1-c) plus c on the diagonal or +-a_k*s off it, evaluated left to right with NumPy's own promotion: the axis
+    components are float32 scalars, so with a float32 angle everything stays float32, and with a Python / float64 angle the
+    products of two axis components are float32 and everything touching cos/sin is float64 -- the same under NumPy 1 and 2,
+    and bit-identical to the reference's own rotate() (tests/golden/host_math_reference.npz)."""
+    c, s = np.cos(angle), np.sin(angle)
+    if not (isinstance(c, np.floating) and c.dtype == np.float32):
+        c, s = np.float64(c), np.float64(s)
+    a = [np.float32(t) for t in to_array(axis)]
     k = 1 - c
-    m = np.empty((4, 4), dtype=np.float64)
-    for i in range(3):          # row i, column j:  a_j*a_i*(1-c) + (c on the diagonal | +-a_k*s off it)
-        for j in range(3):
-            m[i, j] = np.float64(ax[j] * ax[i]) * k
+    sign = ((0, 1, -1), (-1, 0, 1), (1, -1, 0))     # sign of a_k * s at (row i, column j), k the third index
+    m = []
     for i in range(3):
-        m[i, i] += c
-    x, y, z = (np.float64(t) for t in ax)
-    m[0, 1] += z * s; m[0, 2] -= y * s
-    m[1, 0] -= z * s; m[1, 2] += x * s
-    m[2, 0] += y * s; m[2, 1] -= x * s
-    m[3, :] = (0, 0, 0, 1); m[:3, 3] = 0
-    return make_float4x4(*m.ravel().tolist())
+        for j in range(3):
+            term = a[j] * a[i] * k
+            m.append(term + c if i == j else (term + a[3 - i - j] * s if sign[i][j] > 0 else term - a[3 - i - j] * s))
+        m.append(0)
+    return make_float4x4(*[float(t) for t in m], 0.0, 0.0, 0.0, 1.0)
 
 
 def rotate(angle, axis):
-    """Axis-angle rotation.  NumPy-1 semantics of the reference expression: products of two float32 axis
-    components stay float32, everything touching cos/sin is float64, one rounding to float32 at the end.
-    Scalar arithmetic (see _r32): a tutorial frame calls this once and the array version costs ~25 us."""
+    """Axis-angle rotation with the reference's arithmetic (see _rotate_numpy), on Python scalars with explicit float32
+    roundings (see _r32): a tutorial frame calls this once and the NumPy-scalar version costs ~25 us."""
     if not (isinstance(axis, np.ndarray) and axis.dtype == float3 and axis.shape == ()):
         return _rotate_numpy(angle, axis)
-    c, s = float(np.cos(angle)), float(np.sin(angle))
+    c, s = np.cos(angle), np.sin(angle)
+    f32 = isinstance(c, np.floating) and c.dtype == np.float32
+    c, s = float(c), float(s)
     x, y, z, _ = axis.item()
-    k = 1 - c
     xx, yy, zz, xy, xz, yz = _r32(x * x), _r32(y * y), _r32(z * z), _r32(x * y), _r32(x * z), _r32(y * z)
+    if f32:     # float32 angle: every operation rounds to float32
+        k = _r32(1 - c)
+        xs, ys, zs = _r32(x * s), _r32(y * s), _r32(z * s)
+        r = _r32
+        return make_float4x4(r(r(xx * k) + c), r(r(xy * k) + zs), r(r(xz * k) - ys), 0.0,
+                             r(r(xy * k) - zs), r(r(yy * k) + c), r(r(yz * k) + xs), 0.0,
+                             r(r(xz * k) + ys), r(r(yz * k) - xs), r(r(zz * k) + c), 0.0,
+                             0.0, 0.0, 0.0, 1.0)
+    k = 1 - c
     return make_float4x4(xx * k + c, xy * k + z * s, xz * k - y * s, 0.0,
                          xy * k - z * s, yy * k + c, yz * k + x * s, 0.0,
                          xz * k + y * s, yz * k - x * s, zz * k + c, 0.0,

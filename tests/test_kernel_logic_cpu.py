@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_raycast_kernels_on_the_cpu_emulator():
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raycast
-    assert check_raycast.main(600, 64, 32) == 0
+    assert check_raycast.main(600, 64, 32, quick=True) == 0
 
 
 @pytest.mark.timeout(600)
@@ -22,7 +22,7 @@ def test_raycast_kernel_edge_cases_on_the_cpu_emulator():
     """camera inside the mesh (unbounded rectangles), single-triangle scene, sub-rectangle with a pitch, no cull rectangle"""
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raycast
-    assert check_raycast.edges() == 0
+    assert check_raycast.edges(quick=True) == 0
 
 
 @pytest.mark.timeout(600)
@@ -30,7 +30,7 @@ def test_raster_kernels_on_the_cpu_emulator():
     """raster_kernel / coverage_kernel / resolve_kernel / points, lesson08 + lesson09, clipping camera, composing draws"""
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_raster
-    assert check_raster.main(900, 80, 48) == 0
+    assert check_raster.main(900, 80, 48, quick=True) == 0
 
 
 @pytest.mark.timeout(600)
@@ -39,4 +39,4 @@ def test_bvh_builders_on_the_cpu_emulator():
     triangle), and the emulated traversal over them reproduces the oracle's hits"""
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_bvh
-    assert check_bvh.main(300, 48, 32) == 0
+    assert check_bvh.main(300, 48, 32, quick=True) == 0

@@ -54,7 +54,7 @@ def validate_tree(nodes, tris, n, label):
     return height
 
 
-def main(n_tris=700, W=64, H=40):
+def main(n_tris=700, W=64, H=40, quick=False):
     import emu_build
     import oracle
     import rendering as ren
@@ -88,6 +88,8 @@ def main(n_tris=700, W=64, H=40):
         rr = oracle.primary_rays(cam, W, H)
         ref = oracle.raycast_brute(rows, rr, indices=idx)
         for builder, bname in ((0, "LBVH (Karras)"), (1, "PLOC")):
+            if quick and builder == 1 and label not in ("soup", "one triangle"):
+                continue            # PLOC is ~500 launches per build: the CPU test suite keeps two of its four cases
             t0 = time.time()
             nodes = np.zeros(int(B.rt_bvh_node_bytes(T)) // 4, np.float32)
             tris = np.zeros(int(B.rt_bvh_tri_bytes(T)) // 4, np.float32)

@@ -21,7 +21,7 @@ sys.path.insert(0, HERE)
 os.environ.setdefault("RENDERTOY_B200_HOST_BUFFERS", "1")
 
 
-def main(n_tris=1200, W=96, H=64):
+def main(n_tris=1200, W=96, H=64, quick=False):
     import emu_build
     import oracle
     from oracle import host_math as hm
@@ -61,11 +61,15 @@ def main(n_tris=1200, W=96, H=64):
             "far, odd phase": (hm.rotate(2.1, (0, 1, 0)), hm.look_at((0, 0.3, 2), (0, 0, 0), (0, 1, 0))),
             "inside the mesh (near-plane clipping)": (hm.rotate(4.5, (0, 1, 0)), hm.look_at((0.12, 0.32, 0.3), (0, 0, 0), (0, 1, 0)))}
     ok = True
+    if quick:       # the CPU test suite: the lesson camera and the clipping one
+        cams.pop("far, odd phase")
     for cname, (Wm, Vm) in cams.items():
         P = hm.perspective(aspect_ratio=W / H)
         gl = np.concatenate([Wm.ravel(), Vm.ravel(), P.ravel()]).astype(np.float32)
         for shader in (8, 9):
             for mode in ("two draws", "points"):
+                if quick and mode == "points" and (shader == 9 or cname != "lesson camera"):
+                    continue
                 t0 = time.time()
                 key = np.zeros(W * H, np.uint64)
                 bgra = np.full((H, W), 0x55555555, np.uint32)

@@ -64,7 +64,7 @@ def rays_traced_tiles(cull, W, H):
     return ((x1 >> 3) - (x0 >> 3) + 1) * ((y1 >> 2) - (y0 >> 2) + 1)
 
 
-def main(n_tris=1500, W=96, H=64):
+def main(n_tris=1500, W=96, H=64, quick=False):
     import emu_build
     import oracle
     import rendering as ren
@@ -88,7 +88,7 @@ def main(n_tris=1500, W=96, H=64):
     nrm4 = np.zeros((3 * T, 4), np.float32); nrm4[:, :3] = rows[:, 4:7]
     vnodes = np.zeros(int(L.rt_raycast_view_node_bytes(T)), np.uint8)
     ok = True
-    for lesson, t in ((6, 0.5), (8, 2.2)):
+    for lesson, t in (((8, 2.2),) if quick else ((6, 0.5), (8, 2.2))):
         world, view, proj = scenes.lesson_camera(ren, lesson, t, W, H)
         cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
         ref_t, ref_id, ref_u, ref_v = oracle.raycast_brute(rows, oracle.primary_rays(cam, W, H))
@@ -126,7 +126,7 @@ def main(n_tris=1500, W=96, H=64):
     return 0 if ok else 1
 
 
-def edges():
+def edges(quick=False):
     """Edge cases through every variant: the camera inside the mesh (unbounded rectangles: the region walk cannot stop early
     and must fall back), a single-triangle scene (the one-node tree with an empty second child), a sub-rectangle of the frame
     with a pitch, and no cull rectangle."""
@@ -142,9 +142,9 @@ def edges():
     L.rt_raycast_view_node_bytes.argtypes = [I64]
     L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
     L.rt_last_error.restype = C.c_char_p
-    W, H = 72, 44
+    W, H = (56, 36) if quick else (72, 44)
     ok = True
-    rows_big = scenes.dragon(900)
+    rows_big = scenes.dragon(350 if quick else 900)
     one = rows_big[:3].copy()
     one[:, 0:3] = np.float32([[-0.3, -0.2, 0.1], [0.35, -0.25, 0.0], [0.05, 0.3, -0.1]])
     inside = np.array([0, 0, 0, 0.8, 0, 0, 0, 0.6, 0, 0, 0, 1], np.float32)
@@ -174,6 +174,8 @@ def edges():
         ref_px = oracle.shade_hits(8, rows, ref_id, ref_u, ref_v).reshape(h, w, 4)
         for label, passes, a_max, use_view in [("3-D", 0, 0.0, False), ("packets", 0, 0.0, True), ("refit x3", 3, 0.0, True),
                                                ("region 8", 0, 8.0, True), ("region 8 + refit x3", 3, 8.0, True), ("region 0.5", 0, 0.5, True)]:
+            if quick and label in ("refit x3", "region 8"):
+                continue
             L.rt_raycast_set_view_refit(passes); L.rt_raycast_set_region_traversal(a_max)
             hits = np.full((w * h, 4), np.nan, np.float32)
             frame = np.full((H, W), 0x55555555, np.uint32)

@@ -165,7 +165,8 @@ class _Storage:
         else:
             dev = dev or device()
             self.tensor = torch.zeros(max(self.nbytes, 1), dtype=torch.uint8, device=dev)
-        self.host = np.zeros(self.nbytes, dtype=np.uint8) if self.nbytes <= _HOST_SHADOW_MAX else None
+        # adopted memory has contents (and writers: rt_copy_rect, peer kernels) this object knows nothing about: no shadow
+        self.host = np.zeros(self.nbytes, dtype=np.uint8) if (self.nbytes <= _HOST_SHADOW_MAX and tensor is None) else None
         self.host_valid = self.host is not None
         self.dev_valid = True
         self.version = 0
@@ -470,6 +471,7 @@ class Image:
 
 
 def create_image2d(width: int, height: int, dtype: np.dtype):
+    dtype = np.dtype(dtype)     # the reference's table is keyed by the np.float32 CLASS (:343-349): accept both spellings
     assert dtype in _IMAGE_FORMATS, "Unsupported dtype for image format"
     return Image(width, height, dtype)
 

@@ -64,6 +64,8 @@ def _check_layout(dtype, expected, what):
 class Raster:
 
     def __init__(self, render_target, vertex_shader, vertex_shader_globals, fragment_shader, fragment_shader_globals):
+        # both resolve paths store packed BGRA8 words (the presenter's CL_BGRA / UNORM_INT8 image, _core.py:340)
+        assert getattr(render_target, "is_bgra8", False), "Raster renders into a BGRA8 image (create_image2d(w, h, RGBA))"
         self._render_target = render_target
         n_pixels = render_target.width * render_target.height
         # depth lives in the high word of a 64-bit key per pixel; starts at 0 like the reference's zero-filled

@@ -32,6 +32,10 @@ struct __align__(8) clf2 { union { float s[2]; struct { float x, y; }; }; };
 struct __align__(8) cli2 { union { int s[2]; struct { int x, y; }; }; };
 struct __align__(16) cli3 { union { int s[4]; struct { int x, y, z; }; }; };
 struct __align__(16) cli4 { union { int s[4]; struct { int x, y, z, w; }; }; };
+// uintN: CUDA's built-in uint3 is 12 bytes / 4-byte aligned, OpenCL's is 16 / 16 like the host dtype (rendering/_core.py:110)
+struct __align__(8) clu2 { union { unsigned s[2]; struct { unsigned x, y; }; }; };
+struct __align__(16) clu3 { union { unsigned s[4]; struct { unsigned x, y, z; }; }; };
+struct __align__(16) clu4 { union { unsigned s[4]; struct { unsigned x, y, z, w; }; }; };
 struct __align__(16) clf3 {
     union { float s[4]; struct { float x, y, z; }; ClSwz<clf2, float, 4, 0, 1> xy; };
 };
@@ -239,3 +243,6 @@ __device__ inline clf4 cl_sample2D_linear(unsigned long long pool, const TEX &t,
 #define int2 cli2
 #define int3 cli3
 #define int4 cli4
+#define uint2 clu2
+#define uint3 clu3
+#define uint4 clu4

@@ -266,3 +266,23 @@ def test_sample2D_linear_against_numpy(ren, linear_kernel):
     assert np.allclose(lin, want, atol=1e-6)
     k = tw * th
     assert np.allclose(lin[:k], tex.reshape(-1, 4), atol=1e-6) and np.array_equal(near[:k], tex.reshape(-1, 4))
+
+
+def test_struct_with_uint_vectors_keeps_the_host_layout(ren):
+    """uint2/uint3/uint4 struct fields: OpenCL's 16-byte uint3, not CUDA's 12-byte built-in (the static_assert in the
+    generated program checks sizeof against the host dtype)."""
+    @ren.kernel_struct
+    class UIntBag:
+        a: ren.uint3
+        b: ren.uint2
+        c: ren.uint4
+        d: np.uint32
+
+    @ren.kernel_main
+    def uint_bag_sum(bags: [UIntBag], out: [np.uint32]):
+        """
+        UIntBag b = bags[thread_id];
+        out[thread_id] = b.a.x + b.a.y + b.a.z + b.b.x + b.b.y + b.c.w + b.d;
+        """
+    from rendering import _dsl
+    assert _dsl.compile_program(_dsl.program_source(uint_bag_sum))

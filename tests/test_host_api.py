@@ -465,3 +465,37 @@ def test_host_math_equals_the_reference_run(ren):
     assert same(np.array([ren.dot(f3(a), f3(b)) for a, b in zip(z["dot_a"], z["dot_b"])]), z["dot"])
     assert same(np.stack([flat(ren.matmul(ren.scale(1.0), ren.rotate(float(t), ren.make_float3(0, 1, 0)))) for t in z["world_t"]]), z["world"])
     assert same(np.stack([hm.matmul(hm.scale(1.0), hm.rotate(float(t), (0, 1, 0))).ravel() for t in z["world_t"]]), z["world"])
+
+
+def test_every_image_format_can_be_created_with_either_dtype_spelling(ren):
+    """create_image2d with each key of get_valid_image_formats(), and with the np.float32 CLASS the reference's table is
+    keyed by (rendering/_core.py:343-349)."""
+    from rendering import _core
+    for fmt in _core.get_valid_image_formats():
+        im = ren.create_image2d(6, 4, fmt)
+        assert im.shape == (6, 4)
+        with ren.mapped(im) as m:
+            assert m.shape[:2] == (4, 6)
+    im = ren.create_image2d(6, 4, np.float32)
+    with ren.mapped(im) as m:
+        assert m.shape == (4, 6) and m.dtype == np.float32
+
+
+def test_image_on_adopted_memory_reads_that_memory(ren):
+    """Image(..., memory=tensor) (a FrameStore slot): reads see what the memory holds, also after somebody else wrote it."""
+    import torch
+    from rendering import _core
+    mem = torch.full((8 * 4 * 4,), 9, dtype=torch.uint8, device=_core.device())
+    im = ren.Image(8, 4, _core.RGBA, memory=mem)
+    assert int(im.get()[0, 0, 0]) == 9
+    mem.fill_(5)        # an external writer (rt_copy_rect, a peer kernel)
+    assert int(im.get()[3, 7, 3]) == 5
+    with ren.mapped(im) as m:
+        m[0, 0, 0] = 1
+    assert int(mem[0]) == 1 and int(mem[1]) == 5
+
+
+def test_raster_refuses_a_render_target_it_cannot_write(ren):
+    from rendertoy_b200 import lessons
+    with pytest.raises(AssertionError):
+        lessons.build_lesson08(ren, ren.create_image2d(8, 8, ren.float4))

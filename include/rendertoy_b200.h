@@ -85,12 +85,19 @@ int rt_raster_write_depth(void *d_key, int64_t n_pixels, const void *d_depth_u32
  *   clear_rgba       NULL, or 4 floats: a clear(render_target, rgba) the caller deferred; folded into the resolve kernel
  *                    (pixels no primitive wins are written with it) instead of a separate fill launch
  *   clear_depth      non-zero: a deferred clear(depth_buffer, v) with v's bits in clear_depth_bits; executed first
+ *   owner            NULL (the whole frame), or 7 ints {x0, y0, x1, y1, stripe_rows, stripe_mod, stripe_rem}: the pixels this
+ *                    call may touch -- the inclusive rect and, inside it, the row stripes s = y / stripe_rows with
+ *                    s % stripe_mod == stripe_rem (stripe_mod = 1: a plain scissor rect).  This is how one frame is split
+ *                    over GPUs by image-space tiles (the reference is single-device, rendering/_core.py:10-11):
+ *                    every rank draws the whole mesh with its own `owner`; owned pixels (key, depth, colour, folded clears)
+ *                    end up exactly as without `owner`, all other pixels are not touched.  Primitives that cannot produce a
+ *                    fragment in an owned pixel are dropped at setup, before any coverage work.
  */
 int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int height);
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles,
                              int shader, const float *vs_globals, uint64_t tex_handle, int width, int height,
                              void *d_key, void *d_scratch, int64_t scratch_bytes, void *d_bgra, const float *clear_rgba,
-                             int clear_depth, uint32_t clear_depth_bits, void *stream);
+                             int clear_depth, uint32_t clear_depth_bits, const int32_t *owner, void *stream);
 
 /* ---- Raster.draw_points  (rendering/_raster.py:399-414) -----------------------------------------------------
  * VertexProcess + PointAssembly (z<0 cull, :140-151) + PointRaster (clip-space |x|,|y| <= w, :214-226) + Dehomogenize +
@@ -100,7 +107,7 @@ int64_t rt_raster_points_scratch_bytes(int64_t n_points);
 int rt_raster_draw_points(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_points, int shader,
                           const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key,
                           void *d_scratch, int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth,
-                          uint32_t clear_depth_bits, void *stream);
+                          uint32_t clear_depth_bits, const int32_t *owner, void *stream);
 
 /* ---- textures  (rendering/_core.py:551-578 MemoryPool / create_texture2D, :94-96 sample2D) ---------
  * Point-sampled float4 CUDA texture object over caller-owned linear device memory (row 0 first).
@@ -143,16 +150,15 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
  * d_view_nodes: NULL, or rt_raycast_view_node_bytes(n_triangles) of 16-byte aligned device scratch: the call then
  * first projects every BVH node into this camera's screen space (one small kernel) and the traversal tests pixels
  * against screen rectangles instead of rays against boxes -- same hits, fewer instructions per node.  The scratch is
- * per call: concurrent calls on different streams need different buffers. */
+ * per call: concurrent calls on different streams need different buffers.
+ * stripes: NULL, or 3 ints {rows, mod, rem} (rows a multiple of 8, y0 a multiple of 8): the image-space partition of one
+ * frame over `mod` GPUs -- frame rows are grouped from y = 0 into stripes of `rows` rows and only the stripes
+ * s with s % mod == rem are traced, cleared and written; every other pixel of the rect (d_hits and d_bgra) is left untouched. */
 int64_t rt_raycast_view_node_bytes(int64_t n_triangles);
-/* EXPERIMENTAL, off by default, not yet measured: after the projection, run `passes` (0..64) in-place passes that tighten
- * every inner child's screen rectangle and depth bound to the union of that child's own two (rt_raycast.cu:
- * view_refit_kernel).  Hits cannot change.  Process-wide setting. */
+/* After the projection, run `passes` (0..64) in-place passes that tighten every inner child's screen rectangle and depth
+ * bound to the union of that child's own two (rt_raycast.cu: view_refit_kernel).  Hits cannot change (tested bit for bit);
+ * node visits drop 11-26 % with 4 passes, each pass costs one more small launch.  Process-wide setting, default 0. */
 int rt_raycast_set_view_refit(int passes);
-/* EXPERIMENTAL, off by default, not yet measured: a_max_tiles > 0 makes rt_raycast_primary's screen-space path walk the top
- * of the tree once per 64 x 16-pixel region (frontier of nodes at most a_max_tiles 8x4-pixel tiles in area, in shared
- * memory) and only the rest per tile (rt_raycast.cu: raycast_region_kernel).  Hits cannot change.  0 = off.  Process-wide. */
-int rt_raycast_set_region_traversal(float a_max_tiles);
 /* Host only, no device work: the cull_rect for rt_raycast_primary -- conservative inclusive pixel rect of the scene box
  * [lo, hi] (3 doubles each) under `camera`, projected corners +- 2 px clamped to the frame.  Returns 1 and fills rect[4],
  * or 0 when there is no usable bound (box reaches the eye plane, singular camera basis, non-finite data): pass NULL then. */
@@ -165,7 +171,7 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
                        int64_t bgra_pitch_px, void *d_stats, const int *cull_rect, int fast_slab,
-                       void *d_view_nodes, void *stream);
+                       void *d_view_nodes, const int32_t *stripes, void *stream);
 
 /* ---- run-time kernels  (rendering/_core.py:247-299: kernel_main / build_kernel_main, one OpenCL program built at
  * first dispatch) --------------------------------------------------------------------------------------------

@@ -5,6 +5,11 @@ through fake_cl, instantiates its Raster with the lesson08 and lesson09 tutorial
 the reference keeps one global OpenCL program per process) and compiles the resulting OpenCL C program text
 for the host CPU.  Outputs: oracle/_ref/clprog_*.{cpp,so} (git-ignored).  Reference sources are read where they
 lie; nothing is copied into the repo.  tests/golden/*.npz are produced by make_golden.py from these programs.
+
+It also byte-compiles the tutorial scripts that drive the two hot paths (tutorials/lesson06, 08, 09) where they lie into
+oracle/_ref/tutorials/*.pyc -- the Python counterpart of compiling a C reference into oracle/_ref/*.so: the GPU box has
+no /root/reference, and tests/test_tutorials_gpu.py executes the UNMODIFIED tutorial programs against this package
+(runpy on the .py here, on the .pyc there).  The .pyc files are git-ignored build outputs like the .so files.
 """
 import glob
 import os
@@ -35,12 +40,28 @@ print("lesson%02d: %d kernels compiled from the reference's program text" % (les
 '''
 
 
+TUTORIALS = ("lesson06_loading_obj", "lesson08_rasterization", "lesson09_texture_mapping")
+
+
+def compile_tutorials():
+    import py_compile
+    out = os.path.join(REPO, "oracle", "_ref", "tutorials")
+    os.makedirs(out, exist_ok=True)
+    for name in TUTORIALS:
+        src = os.path.join(REFERENCE, "tutorials", name + ".py")
+        if os.path.exists(src):
+            py_compile.compile(src, cfile=os.path.join(out, name + ".pyc"), dfile=f"<reference>/tutorials/{name}.py", doraise=True,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    print("tutorials: byte-compiled", ", ".join(TUTORIALS), "-> oracle/_ref/tutorials/")
+
+
 def main():
     if not os.path.isdir(REFERENCE):
         print("reference checkout not present; nothing to build")
         return 0
     for f in glob.glob(os.path.join(REPO, "oracle", "_ref", "clprog_*")):
         os.remove(f)
+    compile_tutorials()
     for lesson in (8, 9):
         code = CHILD.format(repo=REPO, mg=os.path.join(HERE, "make_golden.py"), ref=REFERENCE, lesson=lesson)
         subprocess.check_call([sys.executable, "-c", code], cwd="/tmp")

@@ -27,7 +27,7 @@ SIGNATURES = {
     "rt_raster_read_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_write_depth": (C.c_int, [_VP, _I64, _VP, _VP]),
     "rt_raster_scratch_bytes": (_I64, [_I32, _I64, _I32, _I32]),
-    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, _VP]),
+    "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, C.POINTER(C.c_int), _VP]),
     "rt_raster_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
     "rt_bvh_node_bytes": (_I64, [_I64]),
     "rt_bvh_tri_bytes": (_I64, [_I64]),
@@ -35,10 +35,9 @@ SIGNATURES = {
     "rt_bvh_build": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _I32, _VP]),
     "rt_raycast_rays": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, _VP]),
     "rt_raycast_primary": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _FP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _U64, _VP, _VP,
-                                     _I64, _VP, C.POINTER(C.c_int), _I32, _VP, _VP]),
+                                     _I64, _VP, C.POINTER(C.c_int), _I32, _VP, C.POINTER(C.c_int), _VP]),
     "rt_raycast_view_node_bytes": (_I64, [_I64]),
     "rt_raycast_set_view_refit": (C.c_int, [_I32]),
-    "rt_raycast_set_region_traversal": (C.c_int, [C.c_float]),
     "rt_camera_frame": (C.c_int, [_FP, _FP, _FP, _FP]),
     "rt_raycast_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
     "rt_dsl_compile": (C.c_int, [C.c_char_p, C.POINTER(_U64), C.c_char_p, _I32]),
@@ -56,7 +55,7 @@ SIGNATURES = {
     "rt_peer_close": (C.c_int, [_VP]),
     "rt_copy_rect": (C.c_int, [_VP, _I64, _VP, _I64, _I64, _I64, _VP]),
     "rt_raster_points_scratch_bytes": (_I64, [_I64]),
-    "rt_raster_draw_points": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, _VP]),
+    "rt_raster_draw_points": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, C.POINTER(C.c_int), _VP]),
     "rt_texture_create": (C.c_int, [_VP, _I32, _I32, C.POINTER(_U64)]),
     "rt_texture_destroy": (C.c_int, [_U64]),
 }

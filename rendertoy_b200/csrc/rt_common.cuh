@@ -39,6 +39,44 @@ struct rt_texture {
     int w, h;
 };
 
+// Pixel ownership of an image-space partition ("bin only into owned tiles"; the reference is
+// single-device, rendering/_core.py:10-11).  A rank owns the inclusive pixel rect [x0, x1] x [y0, y1] and, inside it, row
+// stripes: rows are grouped from y = 0 into stripes of `rows` rows, stripe s is owned iff s % mod == rem (mod = 1: the
+// plain rect -- a scissor).  C ABI form: 7 ints {x0, y0, x1, y1, rows, mod, rem}, NULL = the whole frame.
+struct RtOwner {
+    int x0, y0, x1, y1;
+    unsigned rows, mod, rem;
+};
+__host__ __device__ __forceinline__ bool rt_owns_row(const RtOwner &o, int y)
+{
+    return y >= o.y0 && y <= o.y1 && (o.mod == 1u || ((unsigned)y / o.rows) % o.mod == o.rem);
+}
+__host__ __device__ __forceinline__ bool rt_owns(const RtOwner &o, int x, int y) { return x >= o.x0 && x <= o.x1 && rt_owns_row(o, y); }
+// any owned row in [ya, yb]?
+__host__ __device__ __forceinline__ bool rt_owns_any_row(const RtOwner &o, int ya, int yb)
+{
+    ya = ya > o.y0 ? ya : o.y0;
+    yb = yb < o.y1 ? yb : o.y1;
+    if (ya > yb) return false;
+    if (o.mod == 1u) return true;
+    const unsigned sa = (unsigned)ya / o.rows, sb = (unsigned)yb / o.rows;
+    if (sb - sa + 1u >= o.mod) return true;
+    for (unsigned s = sa; s <= sb; ++s)
+        if (s % o.mod == o.rem) return true;
+    return false;
+}
+// owner7 -> RtOwner clipped to the frame; returns 0 (and the whole frame) for NULL, 1 for a partition, -1 for bad values
+static inline int rt_owner_parse(const int32_t *owner7, int width, int height, RtOwner *o)
+{
+    o->x0 = 0; o->y0 = 0; o->x1 = width - 1; o->y1 = height - 1; o->rows = 1u; o->mod = 1u; o->rem = 0u;
+    if (!owner7) return 0;
+    if (owner7[4] < 1 || owner7[5] < 1 || owner7[6] < 0 || owner7[6] >= owner7[5]) return -1;
+    o->x0 = owner7[0] > 0 ? owner7[0] : 0; o->y0 = owner7[1] > 0 ? owner7[1] : 0;
+    o->x1 = owner7[2] < width - 1 ? owner7[2] : width - 1; o->y1 = owner7[3] < height - 1 ? owner7[3] : height - 1;
+    o->rows = (unsigned)owner7[4]; o->mod = (unsigned)owner7[5]; o->rem = (unsigned)owner7[6];
+    return 1;
+}
+
 // normalize((float3)(1,1,1)).x, correctly rounded (lesson08:42)
 #define RT_INV_SQRT3 0.57735026918962576f
 

@@ -30,6 +30,8 @@ struct DrawArgs {
     float half_w, half_h;
     unsigned long long *key;
     float4 *rec;
+    RtOwner own; // pixels this draw may write ...
+    int scissor; // ... 0: the whole frame (no ownership tests anywhere)
 };
 
 // ---- reference arithmetic, restated -----------------------------------------------------------
@@ -171,7 +173,7 @@ struct __align__(16) Slot { // 24 words, read as six 128-bit loads (the last two
     float a1, b1, c1, a2;
     float b2, c2, a3, b3;
     float c3, inv_nx; int off; int sxy;        // sxy = startx | starty << 16
-    int nx_tle; unsigned prim; float h1x, h1y; // nx_tle = nx | tle << 16 | robust << 19 | (s < 0) << 20
+    int nx_tle; unsigned prim; float h1x, h1y; // nx_tle = nx | tle << 16 | robust << 19 | (s < 0) << 20 | local << 21 (scissor)
     float h1z, h2x, h2y, h2z;
     float h3x, h3y, h3z, pad;
 };
@@ -185,9 +187,10 @@ struct WorkCtl { // head of the scratch buffer (zero-filled by the caller once, 
 template <int SHADER> struct RecLayout { static constexpr int F4 = SHADER == RT_SHADER_LESSON08 ? 4 : 6; };
 
 // Exact coverage test + depth atomic for one cell of a primitive (h = dehomogenized vertices in edge order).
+template <bool SC>
 __device__ __forceinline__ void cover_cell(const Edges &e, int col, int row, float h1x, float h1y, float h1z, float h2x,
                                            float h2y, float h2z, float h3x, float h3y, float h3z, unsigned prim,
-                                           unsigned long long *key, int W, int H)
+                                           unsigned long long *key, int W, int H, const DrawArgs &a)
 {
     Cell cl = cell_eval(e, col, row);
     if (!cl.inside) return;
@@ -197,6 +200,7 @@ __device__ __forceinline__ void cover_cell(const Edges &e, int col, int row, flo
     if (hz < 0) return; // DepthTest, _raster.py:85
     int ix = (int)hx, iy = (int)hy; // the INTERPOLATED position picks the pixel (:88-89)
     if (ix < 0 || ix >= W || iy < 0 || iy >= H) return;
+    if (SC && !rt_owns(a.own, ix, iy)) return; // the exact ownership test: on the pixel the fragment lands on
     unsigned long long k64 = ((unsigned long long)__float_as_uint(hz) << 32) | prim;
     atomicMin(key + (size_t)iy * W + ix, k64);
 }
@@ -206,8 +210,9 @@ __device__ __forceinline__ void cover_cell(const Edges &e, int col, int row, flo
 // evaluation differs from it by less than N/2 with N = 2^-20 * sum of term magnitudes (a generous 16 ulp).  Hence if
 // all four corner values exceed N with one sign, every cell's float s has that sign and is non-zero.  Returns
 // 0 (not robust: slivers, NaN/inf), +1 or -1.
-__device__ __forceinline__ int robust_sign(const Edges &e, const BBox &bb)
+__device__ __forceinline__ int robust_sign(const Edges &e, const BBox &bb, float &s_abs_min, float &noise)
 {
+    s_abs_min = 0.0f; noise = INFINITY;
     const float x0 = (float)bb.startx + 0.5f, x1 = (float)(bb.startx + bb.nx - 1) + 0.5f;
     const float y0 = (float)bb.starty + 0.5f, y1 = (float)(bb.starty + bb.ny - 1) + 0.5f;
     const float n = 9.5367431640625e-7f * ((fabsf(e.a1) + fabsf(e.a2) + fabsf(e.a3)) * x1 + (fabsf(e.b1) + fabsf(e.b2) + fabsf(e.b3)) * y1 +
@@ -222,12 +227,13 @@ __device__ __forceinline__ int robust_sign(const Edges &e, const BBox &bb)
         if (!(sv == sv)) return 0;
     }
     if (!(n > 1e-18f) || !(n < INFINITY)) return 0;
-    if (smin > n) return 1;
-    if (smax < -n) return -1;
+    noise = n;
+    if (smin > n) { s_abs_min = smin; return 1; }
+    if (smax < -n) { s_abs_min = -smax; return -1; }
     return 0;
 }
 
-template <int SHADER>
+template <int SHADER, bool SC>
 __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3, unsigned prim, Slot &s)
 {
     dehomogenize(p1, a.half_w, a.half_h);
@@ -236,9 +242,32 @@ __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3
     if (p1.z < 0) return 0; // _raster.py:236
     BBox bb = bbox_setup(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, a.width, a.height);
     if (bb.nx == 0) return 0;
+    if (SC && !rt_owns_any_row(a.own, bb.starty - 1, bb.starty + bb.ny)) return 0; // cheap early out (re-checked below)
     float e1x = p2.x - p1.x, e1y = p2.y - p1.y, e2x = p3.x - p1.x, e2y = p3.y - p1.y;
     if (!((e1x * e2y - e1y * e2x) <= 0)) { VO t = p2; p2 = p3; p3 = t; } // :259-266
     Edges e = edge_setup(p1.x, p1.y, p2.x, p2.y, p3.x, p3.y);
+    float s_abs_min, noise;
+    const int rs = robust_sign(e, bb, s_abs_min, noise);
+    int local = 0;
+    if (SC) {
+        // Ownership is decided per FRAGMENT (cover_cell: the pixel the interpolated position lands on, _raster.py:88-89), so a
+        // cell may only be skipped when its fragment provably lands within a pixel of the cell.  The interpolated position is
+        // px + sum_k (h_k - p)(alpha_k - lambda_k) + O(2^-22 px): the float barycentrics alpha_k = d_k / s are off their real
+        // values lambda_k by at most 2 noise / |s| each (noise bounds the rounding of a float edge sum, see robust_sign), so the
+        // fragment moves by less than 6 noise ext / |s|, ext = the triangle's extent.  With |s| > 8 noise ext that is < 0.75 px
+        // and every cell outside the owned rect grown by one pixel can be dropped: such primitives are "local", their bbox
+        // is clipped (after the 64x64 gate, which the reference evaluates on the screen-clamped bbox) and rows of stripes the
+        // rank does not own are skipped.  Slivers that fail the bound keep their whole bbox; only cover_cell filters them.
+        const float ext = fmaxf(fmaxf(p1.x, fmaxf(p2.x, p3.x)) - fminf(p1.x, fminf(p2.x, p3.x)),
+                                fmaxf(p1.y, fmaxf(p2.y, p3.y)) - fminf(p1.y, fminf(p2.y, p3.y)));
+        local = rs != 0 && s_abs_min > 8.0f * noise * ext;
+        if (local) {
+            const int cx0 = max(bb.startx, a.own.x0 - 1), cx1 = min(bb.startx + bb.nx - 1, a.own.x1 + 1);
+            const int cy0 = max(bb.starty, a.own.y0 - 1), cy1 = min(bb.starty + bb.ny - 1, a.own.y1 + 1);
+            if (cx1 < cx0 || cy1 < cy0 || !rt_owns_any_row(a.own, cy0 - 1, cy1 + 1)) return 0;
+            bb.startx = cx0; bb.starty = cy0; bb.nx = cx1 - cx0 + 1; bb.ny = cy1 - cy0 + 1;
+        }
+    }
 
     float4 *r = a.rec + (size_t)prim * RecLayout<SHADER>::F4;
     r[0] = make_float4(p1.x, p1.y, p1.z, p1.w);
@@ -254,8 +283,8 @@ __device__ __forceinline__ int setup_prim(const DrawArgs &a, VO p1, VO p2, VO p3
     s.a3 = e.a3; s.b3 = e.b3; s.c3 = e.c3;
     s.inv_nx = 1.0f / (float)bb.nx;
     s.sxy = bb.startx | (bb.starty << 16);
-    const int rs = robust_sign(e, bb);
-    s.nx_tle = bb.nx | ((int)e.tle << 16) | (rs != 0 ? 1 << 19 : 0) | (rs < 0 ? 1 << 20 : 0); // nx | tle<<16 | robust<<19 | s<0 <<20
+    // nx | tle<<16 | robust<<19 | s<0 <<20 | local<<21
+    s.nx_tle = bb.nx | ((int)e.tle << 16) | (rs != 0 ? 1 << 19 : 0) | (rs < 0 ? 1 << 20 : 0) | (local ? 1 << 21 : 0);
     s.prim = prim;
     s.h1x = p1.x; s.h1y = p1.y; s.h1z = p1.z;
     s.h2x = p2.x; s.h2y = p2.y; s.h2z = p2.z;
@@ -291,7 +320,8 @@ __device__ __forceinline__ int assemble(const DrawArgs &a, long long t, VO (&q)[
 }
 
 // Exact test for one ring entry (slot << 24 | row_local << 12 | col_local packed by the producer).
-__device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned packed, unsigned long long *key, int W, int H)
+template <bool SC>
+__device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned packed, unsigned long long *key, int W, int H, const DrawArgs &a)
 {
     const float4 *sp = reinterpret_cast<const float4 *>(my_slots + (packed >> 24));
     const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3], s4 = sp[4], s5 = sp[5];
@@ -300,7 +330,7 @@ __device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned p
     Edges e;
     e.a1 = s0.x; e.b1 = s0.y; e.c1 = s0.z; e.a2 = s0.w; e.b2 = s1.x; e.c2 = s1.y;
     e.a3 = s1.z; e.b3 = s1.w; e.c3 = s2.x; e.tle = (unsigned)(nx_tle >> 16) & 7u;
-    cover_cell(e, col, row, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, __float_as_uint(s3.y), key, W, H);
+    cover_cell<SC>(e, col, row, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, __float_as_uint(s3.y), key, W, H, a);
 }
 
 // Coverage of the primitives staged in `my_slots` (compacted, owner lane i holds ny / off of slot i): their rows are
@@ -308,8 +338,9 @@ __device__ __forceinline__ void cover_from_slot(const Slot *my_slots, unsigned p
 // division-free sign test accepts (the float edge functions are monotone in px, so per edge the accepted cells are a
 // half-line: an analytic guess is corrected by evaluating the real predicate), pushes those cells on the warp's
 // candidate stack, and full warps of candidates go through the exact test + depth atomics.
+template <bool SC>
 __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ring, int ny, int off, int total, int lane,
-                                           unsigned long long *key, int W, int H)
+                                           unsigned long long *key, int W, int H, const DrawArgs &a)
 {
     const unsigned FULL = 0xffffffffu, le_mask = (2u << lane) - 1u;
     int started = 0; // compacted primitives whose first row lies before `base`
@@ -326,6 +357,8 @@ __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ri
             const int nx_tle = __float_as_int(sp[3].x), sxy = __float_as_int(s2.w);
             lrow = base + lane - __float_as_int(s2.z);
             hi = (nx_tle & 0xffff) - 1;
+            // a row of a "local" primitive (setup_prim) with no owned row within one pixel produces no owned fragment
+            if (SC && (nx_tle & (1 << 21)) && !rt_owns_any_row(a.own, (sxy >> 16) + lrow - 1, (sxy >> 16) + lrow + 1)) hi = -1;
             if (nx_tle & (1 << 19)) { // sign(s) is one constant over the bbox: exact spans
                 const float sg = (nx_tle & (1 << 20)) ? -1.0f : 1.0f;
                 const float x0 = (float)(sxy & 0xffff) + 0.5f; // px of local column 0
@@ -376,16 +409,16 @@ __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ri
             __syncwarp();
             while (pending >= 32) {
                 pending -= 32;
-                cover_from_slot(my_slots, my_ring[pending + lane], key, W, H);
+                cover_from_slot<SC>(my_slots, my_ring[pending + lane], key, W, H, a);
             }
             __syncwarp();
         }
     }
-    if (lane < pending) cover_from_slot(my_slots, my_ring[lane], key, W, H);
+    if (lane < pending) cover_from_slot<SC>(my_slots, my_ring[lane], key, W, H, a);
 }
 
-template <int SHADER>
-__global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
+template <int SHADER, bool SC>
+__global__ void __launch_bounds__(RW * 32, SC ? 5 : (SHADER == RT_SHADER_LESSON08 ? 7 : 6)) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
 {
     __shared__ Slot slots[RW][32];
     __shared__ unsigned ring[RW][RING];
@@ -406,7 +439,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
         if (k == 1 && !__any_sync(FULL, nprim > 1)) break; // second output triangles: near-plane only
         Slot mine;
         int ncells = 0;
-        if (k < nprim) ncells = setup_prim<SHADER>(a, q[k][0], q[k][1], q[k][2], (unsigned)(2 * t + k), mine);
+        if (k < nprim) ncells = setup_prim<SHADER, SC>(a, q[k][0], q[k][1], q[k][2], (unsigned)(2 * t + k), mine);
 
         // large primitives -> global work queue (falls back to inline if the queue is full)
         const unsigned big = __ballot_sync(FULL, ncells > SMALL_MAX);
@@ -420,10 +453,19 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
                 if (lane >= d) incl += v;
             }
             const int tot = __shfl_sync(FULL, incl, 31);
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->n_items, (unsigned)tot);
+            // claim [base, base + tot) only if it fits: n_items never exceeds the capacity and never shrinks, so every slot
+            // below it is owned by exactly one warp, which fills it before the kernel ends (no give-back, no holes)
+            unsigned base = 0xffffffffu;
+            if (lane == 0) {
+                unsigned seen = *(volatile unsigned *)&ctl->n_items;
+                while ((unsigned long long)seen + (unsigned)tot <= capacity) {
+                    const unsigned prev = atomicCAS(&ctl->n_items, seen, seen + (unsigned)tot);
+                    if (prev == seen) { base = seen; break; }
+                    seen = prev;
+                }
+            }
             base = __shfl_sync(FULL, base, 0);
-            if (base + (unsigned)tot <= capacity) {
+            if (base != 0xffffffffu) {
                 unsigned w = base + (unsigned)(incl - nchunks);
                 if (nchunks) {
                     bigslots[w] = mine; // setup travels with the first item: coverage_kernel recomputes nothing
@@ -431,8 +473,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
                     ncells = 0; // handed over
                 }
             } else if (lane == 0) {
-                atomicSub(&ctl->n_items, (unsigned)tot); // give the reservation back; rasterize inline below
-                atomicAdd(&ctl->overflowed, 1u);
+                atomicAdd(&ctl->overflowed, 1u); // queue full: these primitives are rasterized inline below
             }
         }
 
@@ -459,7 +500,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
         }
         __syncwarp();
 
-        cover_rows(my_slots, my_ring, ny, off, total, lane, a.key, W, H);
+        cover_rows<SC>(my_slots, my_ring, ny, off, total, lane, a.key, W, H, a);
     }
 }
 
@@ -469,7 +510,7 @@ __global__ void __launch_bounds__(RW * 32) raster_kernel(const DrawArgs a, WorkC
 // the reference evaluates a*px + b*py + c as (a*px + b*py) + c, and fl(b*py) does not depend on px).  Lanes
 // sign-test their 4 cells; the survivors of the whole warp are then dealt out one per lane (ballot + find-nth-set)
 // so the exact test -- 3 IEEE divisions, depth, 64-bit atomicMin -- always runs on full warps.
-template <int SHADER>
+template <int SHADER, bool SC>
 __global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items, const Slot *bigslots)
 {
     const unsigned FULL = 0xffffffffu;
@@ -499,7 +540,8 @@ __global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const W
             row = starty + r;
             const float py = (float)row + 0.5f;
             const float t1 = e.b1 * py, t2 = e.b2 * py, t3 = e.b3 * py;
-            const int ncol = min(4, startx + nx - col0);
+            int ncol = min(4, startx + nx - col0);
+            if (SC && (nx_tle & (1 << 21)) && !rt_owns_any_row(a.own, row - 1, row + 1)) ncol = 0; // see setup_prim: "local"
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float px = (float)(col0 + c) + 0.5f;
@@ -523,7 +565,7 @@ __global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const W
                 src = (int)__fns(m, 0, k - before + 1); // lane that owns this candidate
             }
             const int scol = __shfl_sync(FULL, col0, src), srow = __shfl_sync(FULL, row, src);
-            if (act) cover_cell(e, scol + c, srow, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, prim, a.key, W, H);
+            if (act) cover_cell<SC>(e, scol + c, srow, s3.z, s3.w, s4.x, s4.y, s4.z, s4.w, s5.x, s5.y, s5.z, prim, a.key, W, H, a);
         }
     }
 }
@@ -540,6 +582,9 @@ struct ResolveArgs {
     int tex_w, tex_h;
     int clear;         // 1: a clear(render_target) is folded into this draw ...
     uint32_t clear_px; // ... pixels nobody wins get this BGRA8 value
+    RtOwner own;       // pixels this draw may write (resolve, clear colour, key re-arm) ...
+    int scissor;       // ... 0: the whole frame
+    int bx0, by0;      // first 32x32 block of the launch grid (the grid covers the owned rect only)
 };
 
 struct PrimRec { float4 h1, h2, h3; };
@@ -620,13 +665,16 @@ __global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->n_items = 0; // queue drained: re-arm for the next draw
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7), y0 = blockIdx.y * 32 + (wid >> 2) * 16 + (lane >> 3);
+    const int x = (a.bx0 + blockIdx.x) * 32 + (wid & 3) * 8 + (lane & 7), y0 = (a.by0 + blockIdx.y) * 32 + (wid >> 2) * 16 + (lane >> 3);
     if (x >= a.width) return;
+    if (a.scissor && (x < a.own.x0 || x > a.own.x1 || !rt_owns_any_row(a.own, y0, y0 + 12))) return;
     unsigned long long k[4];
+    bool mine[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int y = y0 + 4 * i;
-        k[i] = y < a.height ? __ldcs(a.key + (size_t)y * a.width + x) : ~0ull;
+        mine[i] = y < a.height && (!a.scissor || rt_owns_row(a.own, y));
+        k[i] = mine[i] ? __ldcs(a.key + (size_t)y * a.width + x) : ~0ull;
     }
     // Measured on B200 and NOT adopted (dragon100k, 1080p, frame 96.0 us with this form): 1 or 2 pixels per thread and/or 4-6
     // resident blocks per SM via __launch_bounds__ (64 / 48 / 40 registers): 96.5-114 us -- the register caps spill, and
@@ -634,8 +682,9 @@ __global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const unsigned long long k64 = i == 0 ? k[0] : i == 1 ? k[1] : i == 2 ? k[2] : k[3];
+        const bool own_i = i == 0 ? mine[0] : i == 1 ? mine[1] : i == 2 ? mine[2] : mine[3];
         if ((unsigned)k64 != RT_NO_PRIMITIVE) resolve_pixel<SHADER>(a, x, y0 + 4 * i, k64);
-        else if (a.clear && y0 + 4 * i < a.height) a.bgra[(size_t)(y0 + 4 * i) * a.width + x] = a.clear_px;
+        else if (a.clear && own_i) a.bgra[(size_t)(y0 + 4 * i) * a.width + x] = a.clear_px;
     }
 }
 
@@ -658,6 +707,7 @@ __global__ void __launch_bounds__(256) points_kernel(const DrawArgs a)
     if (v.z < 0) return;
     const int ix = (int)v.x, iy = (int)v.y;
     if (ix < 0 || ix >= a.width || iy < 0 || iy >= a.height) return;
+    if (a.scissor && !rt_owns(a.own, ix, iy)) return;
     atomicMin(a.key + (size_t)iy * a.width + ix, ((unsigned long long)__float_as_uint(v.z) << 32) | (unsigned)i);
 }
 
@@ -666,6 +716,7 @@ __global__ void __launch_bounds__(256) resolve_points_kernel(const ResolveArgs a
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)a.width * a.height) return;
+    if (a.scissor && !rt_owns(a.own, (int)(p % a.width), (int)(p / a.width))) return;
     const unsigned long long k64 = a.key[p];
     const unsigned prim = (unsigned)k64;
     if (prim == RT_NO_PRIMITIVE) {
@@ -704,6 +755,15 @@ __global__ void fill_u32_kernel(uint4 *dst, long long n4, uint32_t v, uint32_t *
     const uint4 vv = make_uint4(v, v, v, v);
     for (; i < n4; i += stride) dst[i] = vv;
     if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = v;
+}
+
+// clear(depth_buffer) under a scissor / stripe ownership: only owned pixels (one block per row of the owned rect)
+__global__ void fill_u64_owned_kernel(unsigned long long *key, int width, const RtOwner own, unsigned long long v)
+{
+    const int y = own.y0 + (int)blockIdx.x;
+    if (!rt_owns_row(own, y)) return;
+    unsigned long long *row = key + (size_t)y * width;
+    for (int x = own.x0 + (int)threadIdx.x; x <= own.x1; x += (int)blockDim.x) row[x] = v;
 }
 
 __global__ void read_depth_kernel(const unsigned long long *key, long long n, uint32_t *out)
@@ -757,14 +817,18 @@ int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scr
     if (da.n_tris > 0) {
         // one warp per 32 triangles, RW warps per block; the hardware block scheduler does the load balancing
         long long blocks = (da.n_tris + RW * 32 - 1) / (RW * 32);
-        raster_kernel<SHADER><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
+        if (da.scissor) raster_kernel<SHADER, true><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
+        else raster_kernel<SHADER, false><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
         RT_CUDA(cudaGetLastError());
         if (cap > 0) {
-            coverage_kernel<SHADER><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
+            if (da.scissor) coverage_kernel<SHADER, true><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
+            else coverage_kernel<SHADER, false><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
             RT_CUDA(cudaGetLastError());
         }
     }
-    dim3 grid((ra.width + 31) / 32, (ra.height + 31) / 32), block(256);
+    ra.bx0 = ra.own.x0 / 32; ra.by0 = ra.own.y0 / 32; // own is the whole frame without a scissor
+    if (ra.own.x1 < ra.own.x0 || ra.own.y1 < ra.own.y0) { ra.bx0 = ra.by0 = 0; ra.own.x1 = ra.own.x0 = 0; ra.own.y1 = ra.own.y0 = 0; ra.own.mod = 2u; ra.own.rem = 1u; ra.own.rows = 1u << 30; } // empty: one block, owns nothing
+    dim3 grid(ra.own.x1 / 32 - ra.bx0 + 1, ra.own.y1 / 32 - ra.by0 + 1), block(256);
     resolve_kernel<SHADER><<<grid, block, 0, st>>>(ra);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
@@ -786,6 +850,21 @@ int rt_raster_clear_depth(void *d_key, int64_t n_pixels, uint32_t depth_bits, vo
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
+
+} // extern "C"
+
+// clear(depth_buffer) folded into a draw: the whole key buffer, or under a scissor only the pixels the draw owns
+static int clear_depth_owned(void *d_key, int width, int height, uint32_t depth_bits, const RtOwner &own, int scissor, void *stream)
+{
+    if (!scissor) return rt_raster_clear_depth(d_key, (int64_t)width * height, depth_bits, stream);
+    if (own.x1 < own.x0 || own.y1 < own.y0) return RT_OK;
+    const unsigned long long v = ((unsigned long long)depth_bits << 32) | 0xFFFFFFFFull;
+    fill_u64_owned_kernel<<<(unsigned)(own.y1 - own.y0 + 1), 256, 0, (cudaStream_t)stream>>>((unsigned long long *)d_key, width, own, v);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+extern "C" {
 
 int rt_raster_clear_color(void *d_bgra, int64_t n_pixels, const float rgba[4], void *stream)
 {
@@ -835,7 +914,7 @@ int64_t rt_raster_scratch_bytes(int shader, int64_t n_triangles, int width, int 
 int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_triangles, int shader,
                              const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_scratch,
                              int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth, uint32_t clear_depth_bits,
-                             void *stream)
+                             const int32_t *owner, void *stream)
 {
     RT_REQUIRE(n_triangles >= 0 && n_triangles < (1ll << 31), "triangle count (primitive ids are 32-bit: 2*t+k)");
     RT_REQUIRE(n_triangles == 0 || (d_pos4 && d_nrm4), "vertex arrays");
@@ -851,14 +930,17 @@ int rt_raster_draw_triangles(const void *d_pos4, const void *d_nrm4, const int32
     da.width = width; da.height = height;
     da.half_w = (float)width * 0.5f; da.half_h = (float)height * 0.5f; // viewport_dim * 0.5f, _raster.py:129
     da.key = (unsigned long long *)d_key; da.rec = (float4 *)((char *)d_scratch + CTL_BYTES);
+    da.scissor = rt_owner_parse(owner, width, height, &da.own);
+    RT_REQUIRE(da.scissor >= 0, "owner: {x0, y0, x1, y1, stripe rows >= 1, stripe mod >= 1, 0 <= stripe rem < mod}");
     ResolveArgs ra;
     ra.ctl = nullptr;
     ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
     ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
     ra.clear = clear_rgba ? 1 : 0;
     ra.clear_px = clear_rgba ? pack_bgra_host(clear_rgba) : 0u;
+    ra.own = da.own; ra.scissor = da.scissor; ra.bx0 = ra.by0 = 0;
     if (clear_depth) { // a pending clear(depth_buffer, v) folded into this call: must precede the coverage atomics
-        int rc = rt_raster_clear_depth(d_key, (int64_t)width * height, clear_depth_bits, stream);
+        int rc = clear_depth_owned(d_key, width, height, clear_depth_bits, da.own, da.scissor, stream);
         if (rc != RT_OK) return rc;
     }
     if (shader == RT_SHADER_LESSON09) {
@@ -875,7 +957,7 @@ int64_t rt_raster_points_scratch_bytes(int64_t n_points) { return (int64_t)CTL_B
 int rt_raster_draw_points(const void *d_pos4, const void *d_nrm4, const int32_t *d_indices, int64_t n_points, int shader,
                           const float *vs_globals, uint64_t tex_handle, int width, int height, void *d_key, void *d_scratch,
                           int64_t scratch_bytes, void *d_bgra, const float *clear_rgba, int clear_depth, uint32_t clear_depth_bits,
-                          void *stream)
+                          const int32_t *owner, void *stream)
 {
     RT_REQUIRE(n_points >= 0 && n_points < 0xFFFFFFFFll, "point count (ids are 32-bit)");
     RT_REQUIRE(n_points == 0 || (d_pos4 && d_nrm4), "vertex arrays");
@@ -890,13 +972,16 @@ int rt_raster_draw_points(const void *d_pos4, const void *d_nrm4, const int32_t 
     da.width = width; da.height = height;
     da.half_w = (float)width * 0.5f; da.half_h = (float)height * 0.5f;
     da.key = (unsigned long long *)d_key; da.rec = (float4 *)((char *)d_scratch + CTL_BYTES);
+    da.scissor = rt_owner_parse(owner, width, height, &da.own);
+    RT_REQUIRE(da.scissor >= 0, "owner: {x0, y0, x1, y1, stripe rows >= 1, stripe mod >= 1, 0 <= stripe rem < mod}");
     ResolveArgs ra;
+    ra.own = da.own; ra.scissor = da.scissor; ra.bx0 = ra.by0 = 0;
     ra.ctl = (WorkCtl *)d_scratch; ra.key = da.key; ra.rec = da.rec; ra.bgra = (uint32_t *)d_bgra; ra.width = width; ra.height = height;
     ra.tex = 0; ra.tex_w = 0; ra.tex_h = 0;
     ra.clear = clear_rgba ? 1 : 0;
     ra.clear_px = clear_rgba ? pack_bgra_host(clear_rgba) : 0u;
     if (clear_depth) {
-        int rc = rt_raster_clear_depth(d_key, (int64_t)width * height, clear_depth_bits, stream);
+        int rc = clear_depth_owned(d_key, width, height, clear_depth_bits, da.own, da.scissor, stream);
         if (rc != RT_OK) return rc;
     }
     const unsigned pblocks = (unsigned)((n_points + 255) / 256), rblocks = (unsigned)(((long long)width * height + 255) / 256);

@@ -207,6 +207,11 @@ struct TraceArgs {
     int cull[4];   // primary mode: inclusive pixel rect [x0, y0, x1, y1] outside of which no ray can hit the scene
     int tt[4];     // primary mode: traced tile rectangle {tile x0, tile y0, tiles wide, tiles high} (8x4-pixel tiles of the rect)
     int trace_blocks; // primary mode: blocks [0, trace_blocks) trace 2x2 tiles each, the rest clear
+    // image-space partition (primary mode): frame rows are grouped into stripes of 8 * st_R rows, a rank owns the stripes
+    // s = rem (mod st_mod); st_mod = 1: everything.  Traced block rows (8 pixel rows each) are enumerated over owned stripes only:
+    // the v-th owned block row of the frame is ((rem + (v / R) * mod) * R + v % R); st_v0 = index of the first one traced.
+    unsigned st_R, st_mod, st_rem, st_v0;
+    int st_fb_base; // frame block row of tile row tt[1]
     unsigned long long *stats; // optional: [0] inner-node visits, [1] triangle tests, [2] rays (instrumented build)
 };
 
@@ -399,6 +404,7 @@ __device__ __forceinline__ uint32_t shade(const TraceArgs &a, const Hit &h)
 // Clear block: four pixel rows of the rect, minus the traced tiles, written as misses.
 __device__ __forceinline__ void clear_band(const TraceArgs &a, int band)
 {
+    if (a.st_mod > 1u && ((unsigned)(a.y0 + band * 4) / (8u * a.st_R)) % a.st_mod != a.st_rem) return; // not this rank's stripe
     const bool traced_band = band >= a.tt[1] && band < a.tt[1] + a.tt[3];
     const int skip0 = traced_band ? a.tt[0] * 8 : a.w, skip1 = traced_band ? (a.tt[0] + a.tt[2]) * 8 : a.w;
     for (int r = 0; r < 4; ++r) {
@@ -437,7 +443,13 @@ __device__ __forceinline__ void clear_band(const TraceArgs &a, int band)
 // sub-pixel triangles leave nothing for a tile to share -- and below ~256k triangles the screen-space packets win anyway);
 // a multiplicative permutation of the launch order, to keep the object's expensive tiles out of the kernel's tail (+-0 %);
 // 32x4-pixel strips per block with colours swapped through shared memory so that every warp stores whole 128-byte rows,
-// meant for frames in another GPU's memory (-5 % locally, +-0 % at N=4 over NVLink: store width is not what binds rank 0).
+// meant for frames in another GPU's memory (-5 % locally, +-0 % at N=4 over NVLink: store width is not what binds rank 0);
+// a two-level walk (round 2, profiles/r02a_ab_experimental.txt): a block owns a region of 8x4 tiles, walks the top of the tree
+// once for the region down to a frontier of nodes <= 2 / 8 / 32 tiles in area (shared memory), then its warps walk each tile
+// from the frontier, nearest candidate first.  Hits identical, 3.6 instead of 18.7 node visits per tile below the frontier --
+// and 299 / 298 / 319 us per cfg4 frame against 170 us (lesson08 camera at 4K: 389 - 413 against 408): the frontier scan
+// (one entry per lane + a warp-min per candidate) and the block-wide breadth-first phase cost more than the repeated top
+// visits, which are the cheap, fully coherent, L1-resident part of the walk.  The code was deleted.
 template <int MODE, bool STATS, bool FMA, bool VIEW>
 __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const TraceArgs a)
 {
@@ -446,7 +458,12 @@ __global__ void __launch_bounds__(TB, RT_RAYCAST_MINB) raycast_kernel(const Trac
     if (MODE) {
         if ((int)blockIdx.x >= a.trace_blocks) { clear_band(a, (int)blockIdx.x - a.trace_blocks); return; }
         const int bw = (a.tt[2] + TILES_BX - 1) / TILES_BX;
-        const int tx = a.tt[0] + TILES_BX * ((int)blockIdx.x % bw) + wid % TILES_BX, ty = a.tt[1] + TILES_BY * ((int)blockIdx.x / bw) + wid / TILES_BX;
+        int brow = (int)blockIdx.x / bw;
+        if (a.st_mod > 1u) { // the brow-th traced block row of this rank -> its place in the frame
+            const unsigned v = a.st_v0 + (unsigned)brow;
+            brow = (int)((a.st_rem + (v / a.st_R) * a.st_mod) * a.st_R + v % a.st_R) - a.st_fb_base;
+        }
+        const int tx = a.tt[0] + TILES_BX * ((int)blockIdx.x % bw) + wid % TILES_BX, ty = a.tt[1] + TILES_BY * brow + wid / TILES_BX;
         if (tx >= a.tt[0] + a.tt[2] || ty >= a.tt[1] + a.tt[3]) return;
         const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
         const bool live = lx < a.w && ly < a.h;
@@ -486,8 +503,25 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
         const int cy1 = (a.cull[3] < a.y0 + a.h - 1 ? a.cull[3] : a.y0 + a.h - 1) - a.y0;
         if (cx1 < cx0 || cy1 < cy0) { a.tt[0] = a.tt[1] = a.tt[2] = a.tt[3] = 0; }
         else { a.tt[0] = cx0 >> 3; a.tt[1] = cy0 >> 2; a.tt[2] = (cx1 >> 3) - a.tt[0] + 1; a.tt[3] = (cy1 >> 2) - a.tt[1] + 1; }
-        a.trace_blocks = ((a.tt[2] + TILES_BX - 1) / TILES_BX) * ((a.tt[3] + TILES_BY - 1) / TILES_BY);
-        const bool all_traced = a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
+        int block_rows = (a.tt[3] + TILES_BY - 1) / TILES_BY;
+        if (a.st_mod > 1u && a.tt[3] > 0) {
+            // block rows must coincide with the frame's 8-row groups (y0 is a multiple of 8: checked by the caller)
+            static_assert(TILES_BY == 2, "stripe partition: a block row is 8 pixel rows");
+            const int t0 = a.tt[1] & ~1, t1 = a.tt[1] + a.tt[3]; // first traced tile row, rounded down to a block row
+            a.tt[3] = t1 - t0; a.tt[1] = t0;
+            a.st_fb_base = a.y0 / 8 + a.tt[1] / 2;
+            const unsigned R = a.st_R, mod = a.st_mod, rem = a.st_rem;
+            auto owned_below = [&](unsigned fb) { // owned block rows of the frame with index < fb
+                const unsigned q = fb / R, r = fb % R;
+                const unsigned full = q > rem ? (q - rem - 1u) / mod + 1u : 0u;
+                return full * R + (q % mod == rem ? r : 0u);
+            };
+            const unsigned fb0 = (unsigned)a.st_fb_base, fb1 = fb0 + (unsigned)((a.tt[3] + 1) / 2);
+            a.st_v0 = owned_below(fb0);
+            block_rows = (int)(owned_below(fb1) - a.st_v0);
+        }
+        a.trace_blocks = ((a.tt[2] + TILES_BX - 1) / TILES_BX) * block_rows;
+        const bool all_traced = a.st_mod == 1u && a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
         blocks = (long long)a.trace_blocks + (all_traced ? 0 : (a.h + 3) >> 2);
     } else {
         blocks = (a.n_rays + TB - 1) / TB;
@@ -497,250 +531,10 @@ int launch_trace_s(TraceArgs &a, cudaStream_t st)
     return RT_OK;
 }
 
-// =====================================================================================================================
-// EXPERIMENTAL two-level packet traversal.  OFF BY DEFAULT, NOT YET RUN ON A GPU: written after the round's GPU budget was
-// spent, from the CPU model in tools/visit_histogram.py and tools/region_experiment.py.  The measured
-// path above is untouched (its SASS is byte-identical with and without this block).
-//
-// Why: a tile packet makes ~19-28 node visits and 60 % of them are at nodes that cover more than 64 tiles -- every one of
-// those tiles repeats them.  Here a block owns a REGION of 8 x 4 tiles (64 x 16 pixels).
-//   phase 1, once per region, all 128 threads: breadth-first walk of the screen-space nodes with the region's rectangle (no
-//            depth culling: nothing is known yet), stopping at children that are leaves or whose rectangle is at most
-//            `a_max` tiles in area.  Those children are the region's FRONTIER (rectangle, depth bound, id) in shared memory.
-//            CPU model, cfg4: 56 node tests per region, frontier 22 entries on average, 99 % below 102.
-//   phase 2, per tile (warps take the region's 32 tiles from a shared counter): lanes test one frontier entry each against
-//            the tile's rectangle; the candidates are then taken nearest first (warp min over the depth bounds' bits), each
-//            entered by the lanes whose pixel lies in its rectangle and whose best hit is not nearer than its bound, and
-//            below it runs the same shared-stack packet walk as trace_view_packet.  CPU model: 7.3 candidates, 3.7 node
-//            visits and 3.5 leaf visits per tile, against 18.7 + 3.5 for the one-level walk.
-// If the frontier or a queue overflows, the frontier becomes {root}: phase 2 is then exactly the one-level walk.
-// Hits cannot differ from the one-level walk: both enter a leaf for a lane iff the lane's pixel passes the rectangle and depth
-// tests of a chain of ancestors that all contain the leaf; the exact test at the leaf is the same code.
-#ifndef RT_REGION_TX
-#define RT_REGION_TX 8
-#endif
-#ifndef RT_REGION_TY
-#define RT_REGION_TY 4
-#endif
-constexpr int REG_TX = RT_REGION_TX, REG_TY = RT_REGION_TY; // tiles per region (-D overrides for A/B builds)
-constexpr int REG_FCAP = 128, REG_QCAP = 256;   // frontier entries / nodes per breadth-first level
-
-float g_region_a_max_tiles = 0.0f; // rt_raycast_set_region_traversal: 0 = off
-
-template <bool STATS>
-__device__ __forceinline__ void walk_view_packet(const TraceArgs &a, int cur, unsigned voters, bool live, float sx, float sy, float ox, float oy,
-                                                 float oz, float dx, float dy, float dz, int4 *wstack, unsigned long long &best, float &tbest,
-                                                 float &bu, float &bv, unsigned &n_nodes, unsigned &n_tests)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int sp = 0;
-    while (voters != 0u) {
-        if (cur >= 0) {
-            if (STATS && ((voters >> lane) & 1u)) ++n_nodes;
-            const float4 *np = reinterpret_cast<const float4 *>(a.vnodes + cur);
-            const float4 r0 = __ldg(np), r1 = __ldg(np + 1), zc = __ldg(np + 2);
-            const bool h0 = live && sx >= r0.x && sx <= r0.y && sy >= r0.z && sy <= r0.w && zc.x <= tbest;
-            const bool h1 = live && sx >= r1.x && sx <= r1.y && sy >= r1.z && sy <= r1.w && zc.y <= tbest;
-            const unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
-            const int c0 = __float_as_int(zc.z), c1 = __float_as_int(zc.w);
-            if (m0 != 0u && m1 != 0u) {
-                const bool swap = zc.y < zc.x;
-                if (lane == 0) wstack[sp] = make_int4(swap ? c0 : c1, (int)(swap ? m0 : m1), __float_as_int(swap ? zc.x : zc.y), 0);
-                __syncwarp();
-                ++sp;
-                cur = swap ? c1 : c0; voters = swap ? m1 : m0;
-                continue;
-            }
-            if (m0 != 0u) { cur = c0; voters = m0; continue; }
-            if (m1 != 0u) { cur = c1; voters = m1; continue; }
-        } else if ((voters >> lane) & 1u) {
-            if (STATS) ++n_tests;
-            const float4 *tp = reinterpret_cast<const float4 *>(a.tris + ~cur);
-            const float4 v0 = __ldg(tp), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-            // Moller-Trumbore, operation for operation as oracle/raycast_oracle.c: rc_moller_trumbore
-            const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
-            const float det = (e1.x * px + e1.y * py) + e1.z * pz;
-            if (det != 0.0f) {
-                const float inv = 1.0f / det;
-                const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
-                const float u = ((tx * px + ty * py) + tz * pz) * inv;
-                if (u >= 0.0f && !(u > 1.0f)) {
-                    const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
-                    const float v = ((dx * qx + dy * qy) + dz * qz) * inv;
-                    if (v >= 0.0f && !(u + v > 1.0f)) {
-                        const float t = ((e2.x * qx + e2.y * qy) + e2.z * qz) * inv;
-                        if (t > 0.0f && t != INFINITY) {
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | __float_as_uint(v0.w);
-                            if (key < best) { best = key; tbest = t; bu = u; bv = v; }
-                        }
-                    }
-                }
-            }
-        }
-        voters = 0u;
-        while (sp > 0) {
-            --sp;
-            const int4 e = wstack[sp];
-            const unsigned m = __ballot_sync(FULL, (((unsigned)e.y >> lane) & 1u) && __int_as_float(e.z) <= tbest);
-            if (m != 0u) { cur = e.x; voters = m; break; }
-        }
-    }
-}
-
-template <int MODE, bool STATS>
-__global__ void __launch_bounds__(TB, 8) raycast_region_kernel(const TraceArgs a, const float a_max_ndc)
-{
-    static_assert(TB == 128, "region kernel: four warps per block");
-    __shared__ float4 f_rect[REG_FCAP];
-    __shared__ float2 f_zi[REG_FCAP]; // (depth bound, child id bits)
-    __shared__ int q[2][REG_QCAP];
-    __shared__ int qn[2], fn, overflow, next_tile;
-    __shared__ int4 wstacks[TB / 32][STACK];
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if ((int)blockIdx.x >= a.trace_blocks) { clear_band(a, (int)blockIdx.x - a.trace_blocks); return; }
-    const int regions_x = (a.tt[2] + REG_TX - 1) / REG_TX;
-    const int tile0x = a.tt[0] + REG_TX * ((int)blockIdx.x % regions_x), tile0y = a.tt[1] + REG_TY * ((int)blockIdx.x / regions_x);
-    const int tiles_w = min(REG_TX, a.tt[0] + a.tt[2] - tile0x), tiles_h = min(REG_TY, a.tt[1] + a.tt[3] - tile0y);
-    if (tiles_w <= 0 || tiles_h <= 0) return;
-    const float kx = 2.0f / (float)a.width, ky = 2.0f / (float)a.height;
-    // the same expressions as the lanes' own sx / sy below, so the region (tile) rectangle contains every pixel centre in it
-    const int px_lo = tile0x * 8, px_hi = min(px_lo + tiles_w * 8, a.w) - 1, py_lo = tile0y * 4, py_hi = min(py_lo + tiles_h * 4, a.h) - 1;
-    const float rsx_lo = ((float)(a.x0 + px_lo) + 0.5f) * kx - 1.0f, rsx_hi = ((float)(a.x0 + px_hi) + 0.5f) * kx - 1.0f;
-    const float rsy_hi = 1.0f - ((float)(a.y0 + py_lo) + 0.5f) * ky, rsy_lo = 1.0f - ((float)(a.y0 + py_hi) + 0.5f) * ky;
-
-    // ---- phase 1: the region's frontier
-    if (tid == 0) { q[0][0] = 0; qn[0] = 1; qn[1] = 0; fn = 0; overflow = 0; next_tile = 0; }
-    __syncthreads();
-    int cur_q = 0;
-    for (int level = 0; level < 4 * RT_BVH_MAX_HEIGHT; ++level) {
-        const int n = min(qn[cur_q], REG_QCAP);
-        if (n == 0) break; // the same shared value for every thread
-        for (int i = tid; i < n; i += TB) {
-            const float4 *np = reinterpret_cast<const float4 *>(a.vnodes + q[cur_q][i]);
-            const float4 r0 = __ldg(np), r1 = __ldg(np + 1), zc = __ldg(np + 2);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float4 rc = c ? r1 : r0;
-                const float z = c ? zc.y : zc.x;
-                const int id = __float_as_int(c ? zc.w : zc.z);
-                if (!(rc.x <= rsx_hi && rc.y >= rsx_lo && rc.z <= rsy_hi && rc.w >= rsy_lo)) continue;
-                if (id < 0 || (rc.y - rc.x) * (rc.w - rc.z) <= a_max_ndc) {
-                    const int k = atomicAdd(&fn, 1);
-                    if (k < REG_FCAP) { f_rect[k] = rc; f_zi[k] = make_float2(z, __int_as_float(id)); }
-                    else overflow = 1;
-                } else {
-                    const int k = atomicAdd(&qn[cur_q ^ 1], 1);
-                    if (k < REG_QCAP) q[cur_q ^ 1][k] = id;
-                    else overflow = 1;
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) qn[cur_q] = 0;
-        cur_q ^= 1;
-        __syncthreads();
-    }
-    if (overflow || qn[cur_q] != 0) { // too much for the shared arrays (or a tree deeper than the level bound): the one-level walk
-        __syncthreads();
-        if (tid == 0) {
-            f_rect[0] = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
-            f_zi[0] = make_float2(0.0f, __int_as_float(0));
-            fn = 1;
-        }
-        __syncthreads();
-    }
-    const int n_front = min(fn, REG_FCAP);
-
-    // ---- phase 2: the tiles
-    const int n_tiles = tiles_w * tiles_h;
-    int4 *wstack = wstacks[wid];
-    for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&next_tile, 1);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= n_tiles) break;
-        const int tx = tile0x + t % tiles_w, ty = tile0y + t / tiles_w;
-        const int lx = tx * 8 + (lane & 7), ly = ty * 4 + (lane >> 3);
-        const bool live = lx < a.w && ly < a.h;
-        const float sx = ((float)(a.x0 + lx) + 0.5f) * kx - 1.0f;
-        const float sy = 1.0f - ((float)(a.y0 + ly) + 0.5f) * ky;
-        const float dx = (a.cam[3] * sx + a.cam[6] * sy) + a.cam[9];
-        const float dy = (a.cam[4] * sx + a.cam[7] * sy) + a.cam[10];
-        const float dz = (a.cam[5] * sx + a.cam[8] * sy) + a.cam[11];
-        const float tsx_lo = ((float)(a.x0 + tx * 8) + 0.5f) * kx - 1.0f, tsx_hi = ((float)(a.x0 + min(tx * 8 + 7, a.w - 1)) + 0.5f) * kx - 1.0f;
-        const float tsy_hi = 1.0f - ((float)(a.y0 + ty * 4) + 0.5f) * ky, tsy_lo = 1.0f - ((float)(a.y0 + min(ty * 4 + 3, a.h - 1)) + 0.5f) * ky;
-        unsigned long long best = ~0ull;
-        float tbest = INFINITY, bu = 0.0f, bv = 0.0f;
-        unsigned n_nodes = 0, n_tests = 0;
-        for (int base = 0; base < n_front; base += 32) {
-            const int e = base + lane;
-            bool cand = false;
-            if (e < n_front) {
-                const float4 rc = f_rect[e];
-                cand = rc.x <= tsx_hi && rc.y >= tsx_lo && rc.z <= tsy_hi && rc.w >= tsy_lo;
-            }
-            // depth bounds are >= 0, so their bits order like their values; the low five bits carry the lane, which makes the
-            // warp minimum name its owner (the order among bounds that differ only there does not matter: it is only an order)
-            unsigned zkey = cand ? ((__float_as_uint(f_zi[e].x) & ~31u) | (unsigned)lane) : 0xffffffffu;
-            unsigned cmask = __ballot_sync(FULL, cand);
-            while (cmask != 0u) {
-                const unsigned znear = __reduce_min_sync(FULL, zkey);
-                if (znear == 0xffffffffu) break; // cannot happen while cmask names a candidate (a bound never has all bits set)
-                const int src = (int)(znear & 31u);
-                if (lane == src) zkey = 0xffffffffu;
-                cmask &= ~(1u << src);
-                const float4 rc = f_rect[base + src];
-                const float2 zi = f_zi[base + src];
-                const bool near_enough = live && zi.x <= tbest;
-                const unsigned voters = __ballot_sync(FULL, near_enough && sx >= rc.x && sx <= rc.y && sy >= rc.z && sy <= rc.w);
-                if (voters != 0u) {
-                    walk_view_packet<STATS>(a, __float_as_int(zi.y), voters, live, sx, sy, a.cam[0], a.cam[1], a.cam[2], dx, dy, dz, wstack, best, tbest,
-                                            bu, bv, n_nodes, n_tests);
-                } else if (__ballot_sync(FULL, live && __uint_as_float(znear & ~31u) <= tbest) == 0u) {
-                    break; // keys ascend and a key's float (low bits cleared) is <= its bound: nothing later in this round can be entered
-                }
-            }
-        }
-        if (STATS && live) {
-            atomicAdd(a.stats, (unsigned long long)n_nodes);
-            atomicAdd(a.stats + 1, (unsigned long long)n_tests);
-            atomicAdd(a.stats + 2, 1ull);
-        }
-        if (live) {
-            Hit h;
-            h.t = tbest; h.u = bu; h.v = bv; h.id = best == ~0ull ? 0xFFFFFFFFu : (unsigned)best;
-            if (a.hits) a.hits[(long long)ly * a.w + lx] = make_float4(h.t, __uint_as_float(h.id), h.u, h.v);
-            if (a.bgra) a.bgra[(long long)ly * a.pitch_px + lx] = shade<MODE == 9 ? RT_SHADER_LESSON09 : RT_SHADER_LESSON08>(a, h);
-        }
-    }
-}
-
-template <int MODE, bool STATS>
-int launch_region(TraceArgs &a, cudaStream_t st)
-{
-    const int cx0 = (a.cull[0] > a.x0 ? a.cull[0] : a.x0) - a.x0, cy0 = (a.cull[1] > a.y0 ? a.cull[1] : a.y0) - a.y0;
-    const int cx1 = (a.cull[2] < a.x0 + a.w - 1 ? a.cull[2] : a.x0 + a.w - 1) - a.x0;
-    const int cy1 = (a.cull[3] < a.y0 + a.h - 1 ? a.cull[3] : a.y0 + a.h - 1) - a.y0;
-    if (cx1 < cx0 || cy1 < cy0) { a.tt[0] = a.tt[1] = a.tt[2] = a.tt[3] = 0; }
-    else { a.tt[0] = cx0 >> 3; a.tt[1] = cy0 >> 2; a.tt[2] = (cx1 >> 3) - a.tt[0] + 1; a.tt[3] = (cy1 >> 2) - a.tt[1] + 1; }
-    a.trace_blocks = ((a.tt[2] + REG_TX - 1) / REG_TX) * ((a.tt[3] + REG_TY - 1) / REG_TY);
-    const bool all_traced = a.tt[0] == 0 && a.tt[1] == 0 && a.tt[2] * 8 >= a.w && a.tt[3] * 4 >= a.h;
-    const long long blocks = (long long)a.trace_blocks + (all_traced ? 0 : (a.h + 3) >> 2);
-    const float a_max_ndc = g_region_a_max_tiles * (8.0f * 2.0f / (float)a.width) * (4.0f * 2.0f / (float)a.height);
-    if (blocks > 0) raycast_region_kernel<MODE, STATS><<<(unsigned)blocks, TB, 0, st>>>(a, a_max_ndc);
-    RT_CUDA(cudaGetLastError());
-    return RT_OK;
-}
-// =====================================================================================================================
-
 template <int MODE>
 int launch_trace(TraceArgs &a, bool fma, cudaStream_t st)
 {
     if constexpr (MODE != 0) {
-        if (a.vnodes && g_region_a_max_tiles > 0.0f) // experimental two-level traversal, off by default
-            return a.stats ? launch_region<MODE, true>(a, st) : launch_region<MODE, false>(a, st);
         if (a.vnodes) return a.stats ? launch_trace_s<MODE, true, false, true>(a, st) : launch_trace_s<MODE, false, false, true>(a, st);
     }
     if (a.stats) return fma ? launch_trace_s<MODE, true, true, false>(a, st) : launch_trace_s<MODE, true, false, false>(a, st);
@@ -800,7 +594,7 @@ int rt_raycast_rays(const void *d_nodes, const void *d_tris, int64_t n_triangles
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4, const void *d_nrm4,
                        const int32_t *d_indices, const float *camera, int width, int height, int x0, int y0, int w, int h, int shader,
                        uint64_t tex_handle, void *d_hits, void *d_bgra, int64_t bgra_pitch_px, void *d_stats,
-                       const int *cull_rect, int fast_slab, void *d_view_nodes, void *stream)
+                       const int *cull_rect, int fast_slab, void *d_view_nodes, const int32_t *stripes, void *stream)
 {
     RT_REQUIRE(d_nodes && d_tris && n_triangles >= 1, "BVH");
     RT_REQUIRE(camera, "camera");
@@ -818,6 +612,12 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
     a.stats = (unsigned long long *)d_stats;
     a.cull[0] = cull_rect ? cull_rect[0] : 0; a.cull[1] = cull_rect ? cull_rect[1] : 0;
     a.cull[2] = cull_rect ? cull_rect[2] : width - 1; a.cull[3] = cull_rect ? cull_rect[3] : height - 1;
+    a.st_R = 1u; a.st_mod = 1u; a.st_rem = 0u; a.st_v0 = 0u; a.st_fb_base = 0;
+    if (stripes && stripes[1] > 1) {
+        RT_REQUIRE(stripes[0] >= 8 && stripes[0] % 8 == 0 && stripes[2] >= 0 && stripes[2] < stripes[1] && y0 % 8 == 0,
+                   "stripes: {rows (multiple of 8), mod, 0 <= rem < mod}, and the pixel rect must start on a multiple of 8 rows");
+        a.st_R = (unsigned)stripes[0] / 8u; a.st_mod = (unsigned)stripes[1]; a.st_rem = (unsigned)stripes[2];
+    }
     if (d_view_nodes) {
         RT_REQUIRE(((uintptr_t)d_view_nodes & 15) == 0, "view nodes must be 16-byte aligned");
         ProjectArgs p = {};
@@ -945,15 +745,6 @@ int rt_raycast_set_view_refit(int passes)
 {
     RT_REQUIRE(passes >= 0 && passes <= 64, "0..64 passes");
     g_view_refit_passes = passes;
-    return RT_OK;
-}
-
-// EXPERIMENTAL (see raycast_region_kernel): a_max_tiles > 0 switches rt_raycast_primary's screen-space path to the two-level
-// traversal with that frontier threshold (8 is what the CPU model was run with); 0 (the default) restores the measured path.
-int rt_raycast_set_region_traversal(float a_max_tiles)
-{
-    RT_REQUIRE(a_max_tiles >= 0.0f && a_max_tiles <= 4096.0f, "frontier threshold in tiles, 0 = off");
-    g_region_a_max_tiles = a_max_tiles;
     return RT_OK;
 }
 

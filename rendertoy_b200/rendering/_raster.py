@@ -74,6 +74,7 @@ class Raster:
         self._depth_buffer = DepthView(self._key_buffer, n_pixels)
         self._fill_mode = FillMode.WIREFRAME
         self._keys_armed = False
+        self._owner = None      # set_scissor(): (c_int * 7) {x0, y0, x1, y1, stripe rows, mod, rem} handed to the native draws
         self._draws = None      # draws since the last clear(render_target): [(vertex buffer, its version, globals)], None = unknown
 
         assert len(vertex_shader.signature) == 2 and vertex_shader.return_annotation is not None, "Vertex shader signature incorrect. Must receive one argument with vertex type and another with globals type, and return another struct"
@@ -183,6 +184,29 @@ class Raster:
     def fill_mode(self, value: FillMode):
         self._fill_mode = value
 
+    # -- image-space partition (not in the reference, which is single-device: rendering/_core.py:10-11) ------------------
+    def set_scissor(self, rect=None, stripes=None):
+        """Restrict what the following draws (and the clears folded into them) may touch: the inclusive pixel rect
+        (x0, y0, x1, y1) and / or the row stripes (rows, mod, rem) -- rows are grouped from y = 0 into stripes of `rows`
+        rows and stripe s is owned iff s % mod == rem, which is how parallel.tile_rects deals one frame out to the ranks
+        ("bin only into owned tiles").  Owned pixels (depth, winner, colour) come out exactly as without a
+        scissor; everything else is left untouched.  set_scissor() with no arguments lifts it."""
+        import ctypes
+        if rect is None and stripes is None:
+            self._owner = None
+            return
+        W, H = self._render_target.width, self._render_target.height
+        x0, y0, x1, y1 = rect if rect is not None else (0, 0, W - 1, H - 1)
+        rows, mod, rem = stripes if stripes is not None else (1, 1, 0)
+        assert rows >= 1 and mod >= 1 and 0 <= rem < mod, "stripes = (rows per stripe, modulus, remainder)"
+        assert self._generic is None, "a scissor / stripe partition needs the built-in (tutorial) shader pairs"
+        self._owner = (ctypes.c_int * 7)(int(x0), int(y0), int(x1), int(y1), int(rows), int(mod), int(rem))
+
+    @property
+    def scissor(self):
+        """None, or (x0, y0, x1, y1, stripe rows, stripe mod, stripe rem) as set by set_scissor()."""
+        return None if self._owner is None else tuple(self._owner)
+
     # -- draws ------------------------------------------------------------------------------------------
     def draw_points(self, vertex_buffer, index_buffer=None):
         """Raster.draw_points (:399-414): one fragment per vertex (or per index), same depth / colour targets."""
@@ -209,7 +233,7 @@ class Raster:
         _native.call("rt_raster_draw_points", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
                      gl, self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
                      self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, clear,
-                     0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
+                     0 if depth_bits is None else 1, depth_bits or 0, self._owner, stream_ptr())
         self._key_buffer.device_written()
         rt._buffer.device_written()
 
@@ -234,7 +258,8 @@ class Raster:
         gathered sparsely (parallel.SparseFrameCopier).  The first query for a mesh version reads its bounds back (a sync)."""
         import ctypes
         W, H = self._render_target.width, self._render_target.height
-        full = (0, 0, W - 1, H - 1)
+        full = (0, 0, W - 1, H - 1) if self._owner is None else \
+            (max(0, self._owner[0]), max(0, self._owner[1]), min(W - 1, self._owner[2]), min(H - 1, self._owner[3]))
         if self._draws is None:
             return full
         x0, y0, x1, y1 = W, H, -1, -1
@@ -247,7 +272,9 @@ class Raster:
                 return full
             if r[2] >= r[0] and r[3] >= r[1]:
                 x0, y0, x1, y1 = min(x0, r[0]), min(y0, r[1]), max(x1, r[2]), max(y1, r[3])
-        return (x0, y0, x1, y1) if x1 >= x0 else (0, 0, -1, -1)
+        if self._owner is not None:     # nothing outside the scissor rect was written
+            x0, y0, x1, y1 = max(x0, self._owner[0]), max(y0, self._owner[1]), min(x1, self._owner[2]), min(y1, self._owner[3])
+        return (x0, y0, x1, y1) if (x1 >= x0 and y1 >= y0) else (0, 0, -1, -1)
 
     def _vs_globals(self):
         """48 floats (World, View, Proj) as a ctypes array: the Transforms struct is three contiguous float4x4 (layout
@@ -288,6 +315,6 @@ class Raster:
         _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
                      gl, self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,
                      self._scratch.ptr, self._scratch.nbytes, rt.raw_ptr, clear,
-                     0 if depth_bits is None else 1, depth_bits or 0, stream_ptr())
+                     0 if depth_bits is None else 1, depth_bits or 0, self._owner, stream_ptr())
         self._key_buffer.device_written()
         rt._buffer.device_written()

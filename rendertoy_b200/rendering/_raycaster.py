@@ -197,7 +197,8 @@ class Raycaster:
 
     # -- fused primary rays -----------------------------------------------------------------------------
     def render(self, render_target, camera, rect=None, shader=_native.SHADER_LESSON08, texture_descriptor=None,
-               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True, view_nodes=None):
+               hits: torch.Tensor = None, frame_size=None, stats: torch.Tensor = None, cull=True, view_nodes=None,
+               stripes=None):
         """Primary rays for `rect` = (x0, y0, w, h) of the frame (default: the whole render target), closest hit,
         shade, write BGRA8 into `render_target` at the rect's position.  camera: 12 floats from camera_frame().
         hits: optional (h*w, 4) float32 tensor to also receive {t, id, u, v}.  render_target may be None when only
@@ -205,6 +206,9 @@ class Raycaster:
         adds {node visits, triangle tests, rays} to it.  cull: skip tracing outside the scene's projected bounds.
         view_nodes: project the BVH into this camera's screen space first and traverse that (default: yes up to
         VIEW_NODES_MAX_TRIANGLES triangles, where the per-frame projection pass pays for itself).
+        stripes: (rows, mod, rem) -- the image-space partition of one frame over `mod` GPUs (parallel.tile_rects): only
+        the row stripes s = y // rows with s % mod == rem are traced and written, in ONE launch (one projection pass per
+        frame and rank, not one per band); all other pixels of the rect are left untouched.
         Returns the inclusive frame-pixel rect (x0, y0, x1, y1) outside of which everything this call wrote is the clear
         colour / a miss (the cull rect clipped to `rect`; x1 < x0 when nothing can be hit) -- what a sparse gather has to move."""
         if render_target is not None:
@@ -220,7 +224,7 @@ class Raycaster:
         if render_target is not None:
             assert render_target.is_bgra8, "render target must be the BGRA8 presenter image"
             # a full-frame render overwrites every pixel: a deferred clear is dropped, otherwise executed first
-            if (x0, y0, w, h) == (0, 0, W, H):
+            if (x0, y0, w, h) == (0, 0, W, H) and (stripes is None or stripes[1] == 1):
                 render_target.take_pending_clear()
             bgra_ptr = render_target.ptr + 4 * (y0 * W + x0)
         cam_c = _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12)
@@ -245,7 +249,8 @@ class Raycaster:
                      self.nrm4.data_ptr(), self._idx_ptr(),
                      cam_c,
                      W, H, x0, y0, w, h, shader, tex, None if hits is None else hits.data_ptr(), bgra_ptr, W,
-                     None if stats is None else stats.data_ptr(), rect_c, fast_slab, vn_ptr, stream_ptr())
+                     None if stats is None else stats.data_ptr(), rect_c, fast_slab, vn_ptr,
+                     None if stripes is None else (ctypes.c_int * 3)(*[int(v) for v in stripes]), stream_ptr())
         if render_target is not None:
             render_target._buffer.device_written()
         return content

@@ -166,3 +166,97 @@ def test_content_rect_holds_everything_drawn(ren):
     with ren.mapped(vb) as m:
         m.view(np.float32).reshape(rows.shape)[0, 0] += 0.0
     assert raster.content_rect == (0, 0, w - 1, h - 1)
+
+
+@pytest.mark.parametrize("lesson,width,height,n_tris,world,cam_lesson", [
+    (8, 1920, 1080, 100_000, 8, 8),      # configs[1] split over 8 ranks, stripes of parallel.BAND rows
+    (9, 1920, 1080, 100_000, 2, 8),
+    (8, 3840, 2160, 100_000, 4, 8),      # the 4K frame of configs[3], frame-filling camera
+    (8, 333, 211, 5_000, 3, 6),
+])
+def test_stripe_partition_equals_the_whole_frame(ren, lesson, width, height, n_tris, world, cam_lesson):
+    """SURVEY.md 8e "bin only into owned tiles": every rank draws the whole mesh with set_scissor(stripes=(BAND, world, rank)).
+    The union of the ranks' owned pixels must equal the unpartitioned draw byte for byte (depth words and BGRA8), and no rank
+    may touch a pixel it does not own (sentinels survive).  Two composing draws per frame."""
+    from rendertoy_b200 import parallel
+    rows_a = scenes.dragon(n_tris)
+    rows_b = scenes.dragon(max(n_tris // 4, 100), seed=3)
+    rows_b[:, 0:3] = rows_b[:, 0:3] * np.float32(0.8) + np.float32(0.05)
+    vbs = [_upload(ren, rows_a), _upload(ren, rows_b)]
+    tex = _texture()
+    cam = scenes.lesson_camera(ren, cam_lesson, 0.7, width, height)
+
+    def build():
+        target = ren.create_presenter(width, height).get_render_target()
+        if lesson == 8:
+            raster, g = lessons.build_lesson08(ren, target)
+        else:
+            raster, g, _, _ = lessons.build_lesson09(ren, target, tex)
+        lessons.set_transforms(ren, g, *cam)
+        return raster
+
+    def frame(raster):
+        ren.clear(raster.get_render_target())
+        ren.clear(raster.get_depth_buffer(), 1.0)
+        for vb in vbs:
+            raster.draw_triangles(vb, None)
+
+    whole = build()
+    frame(whole)
+    depth_ref = whole.get_depth_buffer().get().reshape(height, width)
+    bgra_ref = whole.get_render_target().get().view(np.uint32).reshape(height, width)
+    assert (depth_ref != 0x3F800000).any()
+    depth_sum = np.zeros_like(depth_ref)
+    bgra_sum = np.zeros_like(bgra_ref)
+    yy = np.arange(height)[:, None]
+    for rank in range(world):
+        part = build()
+        # sentinels: a depth the draw would beat everywhere, a colour no shader produces
+        part.get_depth_buffer().set(np.full(width * height, 0x7F7F7F7F, np.uint32))
+        with ren.mapped(part.get_render_target()) as m:
+            m.view(np.uint32)[...] = 0xABCDEF01
+        part.set_scissor(stripes=(parallel.BAND, world, rank))
+        frame(part)
+        d = part.get_depth_buffer().get().reshape(height, width)
+        c = part.get_render_target().get().view(np.uint32).reshape(height, width)
+        owned = np.broadcast_to((yy // parallel.BAND) % world == rank, d.shape)
+        assert (d[~owned] == 0x7F7F7F7F).all() and (c[~owned] == 0xABCDEF01).all(), f"rank {rank} wrote outside its stripes"
+        depth_sum[owned] = d[owned]
+        bgra_sum[owned] = c[owned]
+    assert np.array_equal(depth_sum, depth_ref), f"{int((depth_sum != depth_ref).sum())} depth words differ from the whole frame"
+    assert np.array_equal(bgra_sum, bgra_ref), f"{int((bgra_sum != bgra_ref).sum())} pixels differ from the whole frame"
+
+
+def test_scissor_rect_and_points(ren, oracle):
+    """A plain scissor rect that cuts the mesh: inside == the oracle's full frame, outside untouched; draw_points too;
+    content_rect is clipped to it; lifting the scissor restores whole-frame draws."""
+    w, h = 640, 480
+    rows = scenes.dragon(20_000)
+    vb = _upload(ren, rows)
+    raster, g = lessons.build_lesson08(ren, ren.create_presenter(w, h).get_render_target())
+    lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8, 0.5, w, h))
+    rect = (201, 97, 433, 350)
+    yy, xx = np.mgrid[0:h, 0:w]
+    inside = (xx >= rect[0]) & (xx <= rect[2]) & (yy >= rect[1]) & (yy <= rect[3])
+    for points in (False, True):
+        draw = raster.draw_points if points else raster.draw_triangles
+        ref = (oracle.draw_points if points else oracle.draw_triangles)(8, w, h, rows, lessons.globals_as_floats(g))
+        raster.set_scissor(rect=rect)
+        raster.get_depth_buffer().set(np.full(w * h, 0x7F7F7F7F, np.uint32))
+        with ren.mapped(raster.get_render_target()) as m:
+            m.view(np.uint32)[...] = 0xABCDEF01
+        ren.clear(raster.get_render_target())
+        ren.clear(raster.get_depth_buffer(), 1.0)
+        draw(vb, None)
+        d = raster.get_depth_buffer().get().reshape(h, w)
+        c = raster.get_render_target().get()
+        assert np.array_equal(d[inside], ref.depth[inside]) and np.array_equal(c[inside], ref.bgra[inside])
+        assert (d[~inside] == 0x7F7F7F7F).all() and (c.view(np.uint32).reshape(h, w)[~inside] == 0xABCDEF01).all()
+        cr = raster.content_rect
+        assert cr[0] >= rect[0] and cr[1] >= rect[1] and cr[2] <= rect[2] and cr[3] <= rect[3]
+        raster.set_scissor()
+        ren.clear(raster.get_render_target())
+        ren.clear(raster.get_depth_buffer(), 1.0)
+        draw(vb, None)
+        assert np.array_equal(raster.get_depth_buffer().get().reshape(h, w), ref.depth)
+        assert np.array_equal(raster.get_render_target().get(), ref.bgra)

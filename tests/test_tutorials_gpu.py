@@ -1,0 +1,130 @@
+"""The reference's tutorial programs, UNMODIFIED, executed as programs against this package (north_star: "a tutorial script
+gets the same behaviour with no other changes").
+
+tutorials/lesson08_rasterization.py:13-107 and tutorials/lesson09_texture_mapping.py:13-148 (and lesson06_loading_obj.py, the
+generic-kernel row 8f.1) are run with runpy exactly as `python tutorials/lessonNN.py` would run them: `import rendering`
+resolves to this repo, `lesson_common.ROOT_DIR` points at a temp directory holding a synthesized models/dragon.obj (+ a
+marble2.jpg), the headless Presenter ends the `while True:` loop after RENDERTOY_B200_FRAMES frames and dumps every frame,
+and time.perf_counter is a deterministic clock.  The last frame (render target, depth buffer, dumped PNG) is compared with
+the oracle's restatement of the reference pipeline for the matrices the script left in its globals buffer.
+
+Where the program text comes from: /root/reference/tutorials/*.py when that checkout exists (the build container), else
+oracle/_ref/tutorials/*.pyc -- byte-compiled from those files, in place, by oracle/clshim/build_ref.py (a git-ignored build
+output that travels to the GPU box like oracle/_ref/*.so; the GPU box has no /root/reference).  Nothing here is a retyped copy.
+"""
+import os
+import runpy
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from rendertoy_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = os.environ.get("RENDERTOY_REFERENCE", "/root/reference")
+
+
+def _program(name):
+    src = os.path.join(REFERENCE, "tutorials", name + ".py")
+    if os.path.exists(src):
+        return src
+    pyc = os.path.join(ROOT, "oracle", "_ref", "tutorials", name + ".pyc")
+    if os.path.exists(pyc):
+        return pyc
+    pytest.skip(f"{name}: neither the reference checkout nor oracle/_ref/tutorials/{name}.pyc is here "
+                "(run __graft_entry__.build() where /root/reference exists)")
+
+
+def _run_tutorial(name, tmp_path, monkeypatch, frames=3, n_tris=3000, texture=False):
+    path = _program(name)
+    os.makedirs(tmp_path / "models")
+    scenes.write_obj(str(tmp_path / "models" / "dragon.obj"), scenes.dragon(n_tris, normalise=False))
+    if texture:
+        from PIL import Image
+        rgb = np.random.default_rng(9).integers(0, 256, size=(500, 500, 3), dtype=np.uint8)     # marble2.jpg is 500 x 500
+        Image.fromarray(rgb).resize((125, 125)).resize((500, 500), Image.BICUBIC).save(str(tmp_path / "models" / "marble2.jpg"), quality=92)
+    common = types.ModuleType("lesson_common")        # tutorials/lesson_common.py:10 only computes this path
+    common.ROOT_DIR = str(tmp_path)
+    monkeypatch.setitem(sys.modules, "lesson_common", common)
+    monkeypatch.setenv("RENDERTOY_B200_FRAMES", str(frames))
+    monkeypatch.setenv("RENDERTOY_B200_DUMP", str(tmp_path / "dump"))
+    import time
+    clock = [0.0]
+
+    def fake_clock():
+        clock[0] += 0.173
+        return clock[0]
+    monkeypatch.setattr(time, "perf_counter", fake_clock)
+    ns = runpy.run_path(path, run_name="__main__")
+    dumps = sorted(os.listdir(tmp_path / "dump"))
+    assert len(dumps) == frames, f"the tutorial loop presented {len(dumps)} frames, expected {frames}"
+    from PIL import Image
+    last_png = np.array(Image.open(str(tmp_path / "dump" / dumps[-1])))
+    return ns, last_png, path
+
+
+def _rows(vertex_buffer):
+    return np.ascontiguousarray(vertex_buffer.get()).view(np.float32).reshape(-1, 20)
+
+
+def _globals48(g):
+    v = g.get()
+    return np.concatenate([np.asarray(v[n]).reshape(-1).view(np.float32)[:16] for n in ("World", "View", "Proj")])
+
+
+def test_lesson08_runs_unmodified_and_matches_the_oracle(ren, oracle, tmp_path, monkeypatch):
+    ns, png, path = _run_tutorial("lesson08_rasterization", tmp_path, monkeypatch)
+    raster = ns["raster"]
+    assert raster.shader_id == 8, "the tutorial's shader pair must be recognised (native twins), not take the NVRTC path"
+    rows = _rows(ns["vertex_buffer"])
+    res = oracle.draw_triangles(8, 640, 480, rows, _globals48(ns["shader_globals"]))
+    assert (res.winner != 0xFFFFFFFF).mean() > 0.1
+    assert np.array_equal(raster.get_depth_buffer().get().reshape(480, 640), res.depth)
+    bgra = ns["presenter"].get_render_target().get()
+    assert np.array_equal(bgra, res.bgra)
+    assert np.array_equal(png, res.bgra[:, :, [2, 1, 0]]), "dumped PNG differs from the oracle frame"
+    print("ran", path)
+
+
+def test_lesson09_runs_unmodified_and_matches_the_oracle(ren, oracle, tmp_path, monkeypatch):
+    ns, png, path = _run_tutorial("lesson09_texture_mapping", tmp_path, monkeypatch, texture=True)
+    raster = ns["raster"]
+    assert raster.shader_id == 9
+    rows = _rows(ns["vertex_buffer"])
+    img = ns["image_for_texture"]
+    texf = np.ones((img.shape[0], img.shape[1], 4), np.float32)
+    texf[:, :, 0:3] = img / 255.0
+    res = oracle.draw_triangles(9, 640, 480, rows, _globals48(ns["vertex_shader_globals"]), texture=texf)
+    assert np.array_equal(raster.get_depth_buffer().get().reshape(480, 640), res.depth)
+    assert np.array_equal(ns["presenter"].get_render_target().get(), res.bgra)
+    assert np.array_equal(png, res.bgra[:, :, [2, 1, 0]])
+    assert len(np.unique(res.bgra.reshape(-1, 4), axis=0)) > 500, "the frame should show the texture"
+    print("ran", path)
+
+
+def test_lesson06_runs_unmodified(ren, tmp_path, monkeypatch):
+    """The point splat of lesson06 (a user kernel_main through NVRTC): the covered pixels are those a float32 numpy
+    restatement of the kernel predicts (same matrices; colours of colliding points are a race in the reference too)."""
+    ns, png, path = _run_tutorial("lesson06_loading_obj", tmp_path, monkeypatch, n_tris=6000)
+    rows = _rows(ns["vertex_buffer"])
+    g = _globals48(ns["transform_info"]).reshape(3, 4, 4)
+    H = np.concatenate([rows[:, 0:3], np.ones((rows.shape[0], 1), np.float32)], axis=1).astype(np.float32)
+    for m in g:
+        H = (H[:, :, None] * m[None, :, :]).astype(np.float32)
+        H = ((H[:, 0] + H[:, 1]) + H[:, 2]) + H[:, 3]
+    ndc = (H[:, 0:3] / H[:, 3:4]).astype(np.float32)
+    keep = ~((ndc[:, 0] < -1) | (ndc[:, 1] < -1) | (ndc[:, 2] < 0) | (ndc >= 1).any(axis=1))
+    px = (640 * (ndc[keep, 0].astype(np.float64) * 0.5 + 0.5)).astype(np.int64)
+    py = (480 * (0.5 - ndc[keep, 1].astype(np.float64) * 0.5)).astype(np.int64)
+    want = np.zeros((480, 640), bool)
+    want[py, px] = True
+    got = ns["presenter"].get_render_target().get()[:, :, 3] != 0
+    assert want.sum() > 2000
+    # a point within an ulp of a pixel boundary may land next door (dot() association is the OpenCL compiler's choice)
+    assert (want != got).sum() <= max(4, int(2e-3 * want.sum())), f"{int((want != got).sum())} of {int(want.sum())} splat pixels differ"
+    assert np.array_equal(png[:, :, 0] != 0, (ns["presenter"].get_render_target().get()[:, :, 2] != 0))
+    print("ran", path)

@@ -4,8 +4,8 @@
 
 Runs the source of csrc/rt_raycast.cu on CPU threads (tools/cuda_emu) over a numpy-built PLOC tree in the library's node /
 leaf layout and compares every hit record and shaded pixel with the oracle's brute-force definition, bit for bit, for: the
-measured screen-space packet walk, the experimental refit passes, the experimental two-level region traversal (several
-frontier thresholds, including one that overflows the shared arrays and must fall back), and the per-lane 3-D walk.
+screen-space packet walk, the view-node refit passes, the per-lane 3-D walk, and the stripe partition of one frame over
+several ranks (each rank one launch into the same frame; foreign rows must stay untouched).
 This checks kernel LOGIC only -- it is how code written without GPU time left gets its first run.
 """
 import ctypes as C
@@ -74,10 +74,9 @@ def main(n_tris=1500, W=96, H=64, quick=False):
     L = C.CDLL(emu_build.build("rt_raycast"))
     VP, I64, I32, FP = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_float)
     L.rt_raycast_primary.argtypes = [VP, VP, I64, VP, VP, VP, FP, I32, I32, I32, I32, I32, I32, I32, C.c_uint64, VP, VP, I64, VP,
-                                     C.POINTER(C.c_int), I32, VP, VP]
+                                     C.POINTER(C.c_int), I32, VP, C.POINTER(C.c_int), VP]
     L.rt_raycast_view_node_bytes.restype = I64
     L.rt_raycast_view_node_bytes.argtypes = [I64]
-    L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
     L.rt_last_error.restype = C.c_char_p
     counts = (C.c_ulonglong * 5)()
 
@@ -99,18 +98,26 @@ def main(n_tris=1500, W=96, H=64, quick=False):
         has_cull = L.rt_raycast_screen_bounds(cam.ctypes.data_as(FP), lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)), W, H, cull)
         variants = [("3-D per-lane walk", 0, 0.0, False), ("screen-space packets (measured path)", 0, 0.0, True)]
         variants += [(f"refit x{k}", k, 0.0, True) for k in (1, 4, 16)]
-        variants += [(f"region traversal a_max={a:g}, refit x{k}", k, a, True) for a, k in ((8.0, 0), (2.0, 0), (64.0, 4), (8.0, 16), (0.001, 0))]
-        for label, passes, a_max, use_view in variants:
-            assert L.rt_raycast_set_view_refit(passes) == 0 and L.rt_raycast_set_region_traversal(a_max) == 0
+        # image-space partition: 3 ranks, stripes of 8 rows, each rank one launch into the same frame -> must equal the whole frame
+        variants += [("3 ranks x stripes of 8 rows, packets", 0, 3, True), ("2 ranks x stripes of 16 rows, 3-D walk", 0, 2, False)]
+        for label, passes, ranks, use_view in variants:
+            assert L.rt_raycast_set_view_refit(passes) == 0
             hits = np.full((W * H, 4), np.nan, np.float32)
             bgra = np.full((H, W), 0x55555555, np.uint32)
             stats = np.zeros(3, np.uint64)
             t0 = time.time()
             L.emu_counts_read(counts, 1)
-            rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
-                                      W, H, 0, 0, W, H, 8, 0, hits.ctypes.data, bgra.ctypes.data, W, stats.ctypes.data,
-                                      cull if has_cull else None, 0, vnodes.ctypes.data if use_view else None, None)
-            assert rc == 0, L.rt_last_error()
+            for rank in range(max(ranks, 1)):
+                before_h, before_c = hits.copy(), bgra.copy()
+                stripes = (C.c_int * 3)(8 if ranks == 3 else 16, ranks, rank) if ranks else None
+                rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
+                                          W, H, 0, 0, W, H, 8, 0, hits.ctypes.data, bgra.ctypes.data, W, stats.ctypes.data,
+                                          cull if has_cull else None, 0, vnodes.ctypes.data if use_view else None, stripes, None)
+                assert rc == 0, L.rt_last_error()
+                if ranks:   # a rank writes only rows of its own stripes
+                    yy = np.arange(H)
+                    foreign = np.repeat((yy // stripes[0]) % ranks != rank, W)
+                    ok &= np.array_equal(hits.view(np.uint32)[foreign], before_h.view(np.uint32)[foreign]) and np.array_equal(bgra.ravel()[foreign], before_c.ravel()[foreign])
             L.emu_counts_read(counts, 1)
             tiles = max(rays_traced_tiles(cull if has_cull else None, W, H), 1)
             same = (np.array_equal(hits[:, 0].view(np.uint32), ref_t.view(np.uint32)) and np.array_equal(hits[:, 1].view(np.uint32), ref_id)
@@ -121,14 +128,13 @@ def main(n_tris=1500, W=96, H=64, quick=False):
             print(f"lesson{lesson:02d} {W}x{H} T={T}  {label:42s} hits {'==' if same else '!='} oracle, pixels {'==' if same_px else '!='}; "
                   f"{int(stats[0]) / rays:5.1f} node visits, {int(stats[1]) / rays:4.2f} triangle tests per ray; per traced tile: "
                   f"{counts[0] / tiles:6.1f} votes, {counts[1] / tiles:4.1f} warp-min, {counts[3] / 32 / tiles:6.1f} wide loads ({time.time() - t0:.1f} s)", flush=True)
-    L.rt_raycast_set_view_refit(0); L.rt_raycast_set_region_traversal(0.0)
+    L.rt_raycast_set_view_refit(0)
     print("ALL BIT-EXACT" if ok else "MISMATCH")
     return 0 if ok else 1
 
 
 def edges(quick=False):
-    """Edge cases through every variant: the camera inside the mesh (unbounded rectangles: the region walk cannot stop early
-    and must fall back), a single-triangle scene (the one-node tree with an empty second child), a sub-rectangle of the frame
+    """Edge cases through every variant: the camera inside the mesh (unbounded rectangles), a single-triangle scene (the one-node tree with an empty second child), a sub-rectangle of the frame
     with a pitch, and no cull rectangle."""
     import emu_build
     import oracle
@@ -137,10 +143,9 @@ def edges(quick=False):
     L = C.CDLL(emu_build.build("rt_raycast"))
     VP, I64, I32, FP = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_float)
     L.rt_raycast_primary.argtypes = [VP, VP, I64, VP, VP, VP, FP, I32, I32, I32, I32, I32, I32, I32, C.c_uint64, VP, VP, I64, VP,
-                                     C.POINTER(C.c_int), I32, VP, VP]
+                                     C.POINTER(C.c_int), I32, VP, C.POINTER(C.c_int), VP]
     L.rt_raycast_view_node_bytes.restype = I64
     L.rt_raycast_view_node_bytes.argtypes = [I64]
-    L.rt_raycast_set_region_traversal.argtypes = [C.c_float]
     L.rt_last_error.restype = C.c_char_p
     W, H = (56, 36) if quick else (72, 44)
     ok = True
@@ -172,16 +177,13 @@ def edges(quick=False):
         rr = oracle.primary_rays(cam, W, H, rect=(x0, y0, w, h))
         ref_t, ref_id, ref_u, ref_v = oracle.raycast_brute(rows, rr)
         ref_px = oracle.shade_hits(8, rows, ref_id, ref_u, ref_v).reshape(h, w, 4)
-        for label, passes, a_max, use_view in [("3-D", 0, 0.0, False), ("packets", 0, 0.0, True), ("refit x3", 3, 0.0, True),
-                                               ("region 8", 0, 8.0, True), ("region 8 + refit x3", 3, 8.0, True), ("region 0.5", 0, 0.5, True)]:
-            if quick and label in ("refit x3", "region 8"):
-                continue
-            L.rt_raycast_set_view_refit(passes); L.rt_raycast_set_region_traversal(a_max)
+        for label, passes, use_view in [("3-D", 0, False), ("packets", 0, True), ("refit x3", 3, True)]:
+            L.rt_raycast_set_view_refit(passes)
             hits = np.full((w * h, 4), np.nan, np.float32)
             frame = np.full((H, W), 0x55555555, np.uint32)
             rc = L.rt_raycast_primary(nodes.ctypes.data, tris.ctypes.data, T, pos4.ctypes.data, nrm4.ctypes.data, None, cam.ctypes.data_as(FP),
                                       W, H, x0, y0, w, h, 8, 0, hits.ctypes.data, frame.ctypes.data + 4 * (y0 * W + x0), W, None, None, 0,
-                                      vnodes.ctypes.data if use_view else None, None)
+                                      vnodes.ctypes.data if use_view else None, None, None)
             assert rc == 0, L.rt_last_error()
             same = (np.array_equal(hits[:, 0].view(np.uint32), ref_t.view(np.uint32)) and np.array_equal(hits[:, 1].view(np.uint32), ref_id)
                     and np.array_equal(hits[:, 2].view(np.uint32), ref_u.view(np.uint32)) and np.array_equal(hits[:, 3].view(np.uint32), ref_v.view(np.uint32)))
@@ -190,7 +192,7 @@ def edges(quick=False):
             same_px = np.array_equal(got_px, ref_px) and bool((untouched == 0x55555555).all())
             ok &= same and same_px
             print(f"{name:34s} {label:22s} hits {'==' if same else '!='} oracle, pixels {'==' if same_px else '!='} ({int((ref_id != 0xFFFFFFFF).sum())} of {w * h} rays hit)", flush=True)
-    L.rt_raycast_set_view_refit(0); L.rt_raycast_set_region_traversal(0.0)
+    L.rt_raycast_set_view_refit(0)
     print("EDGE CASES BIT-EXACT" if ok else "EDGE CASE MISMATCH")
     return 0 if ok else 1
 

@@ -38,10 +38,6 @@ if __name__ == "__main__":
         from rendertoy_b200 import _native
         _native.call("rt_raycast_set_view_refit", int(os.environ["RT_VIEW_REFIT"]))
         print("view refit passes:", os.environ["RT_VIEW_REFIT"])
-    if os.environ.get("RT_REGION_AMAX"):     # experimental two-level traversal (rt_raycast_set_region_traversal), A/B by hand
-        from rendertoy_b200 import _native
-        _native.call("rt_raycast_set_region_traversal", float(os.environ["RT_REGION_AMAX"]))
-        print("region traversal, frontier threshold (tiles):", os.environ["RT_REGION_AMAX"])
     mode = sys.argv[1] if len(sys.argv) > 1 else ""
     fr = 3 if mode == "ncu" else (40 if mode == "ab" else 20)     # ncu: few launches to profile; ab: the two 4K frames only, 40 frames each
     run(100_000, 3840, 2160, 6, fr); sys.stdout.flush()

@@ -1,21 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of rendertoy_b200 (contract: see DESIGN.md "Measurement").
+"""bench.py -- headline benchmark of rendertoy_b200 (contract: DESIGN.md section 5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--path raycast|raster]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-BASELINE.json's metric has two halves; each is measured on the config it is quoted on, one JSON line:
+BASELINE.json's metric has two halves; each is measured on the config it is quoted on, ONE JSON line:
 
-  primary    "Mrays/s closest-hit (dragon, 4K)"  -> configs[3]: dragon100k, 3840x2160, lesson06 camera orbit,
-             fused primary rays + closest hit + Lambert shade, frames split across ranks, gathered to rank 0
-  secondary  "Mtris/s raster"                    -> configs[1]: dragon100k, 1920x1080, lesson08 shaders,
-             clear + clear + draw_triangles per frame (reported under "secondary" in the same line)
+  primary     "Mrays/s closest-hit (dragon, 4K)" -> configs[3]: dragon100k, 3840x2160, lesson06 camera orbit, fused primary
+              rays + closest hit + Lambert shade.  Animation batch: frames k = rank (mod N), gathered to rank 0 (weak scaling)
+  secondary   "Mtris/s raster"                   -> configs[1]: dragon100k, 1920x1080, lesson08 shaders, clear + clear +
+              draw_triangles per frame, same partition
+  tiles       configs[3] AS WRITTEN: every 4K frame split over the N ranks by image-space row stripes (parallel.BAND rows,
+              stripe s -> rank s % N), stripes gathered into rank 0's frame (strong scaling); same for the raster frame
+  config4     configs[4]: the 10M-triangle instanced scene, 256-frame orbit at 1080p, raster + ray cast, frames k = rank (mod N)
 
-A step = FRAMES_PER_RANK frames per rank of the orbit animation (weak scaling: per-GPU work is fixed).
-`value` = device-timed whole-job throughput with mesh/BVH resident; `e2e` = the same work driven through the
-public `rendering` API with host-side inputs and every frame read back to pinned host memory.
-`--impl reference` times the CPU oracle (oracle/: the restated reference pipeline; the reference has no ray
-caster, so that half is our CPU BVH definition) on the host cores -- it is a baseline, not the target.
+A step = RAY_FRAMES (RAS_FRAMES) frames per rank, so that K = 10 steps keep the GPU busy for >= 0.5 s.  `value` is device-timed
+whole-job throughput with mesh/BVH resident; `e2e` is the same work driven through the public `rendering` API with host-side
+inputs and every frame read back to pinned host memory.  `--impl reference` times the CPU oracle (oracle/: the restated reference
+raster pipeline; the reference has no ray caster, so that half is our CPU BVH definition) on all host cores.
 """
 import argparse
 import json
@@ -33,11 +35,23 @@ sys.path.insert(0, ROOT)
 N_TRIS = 100_000
 RAY_W, RAY_H = 3840, 2160
 RAS_W, RAS_H = 1920, 1080
-FRAMES_PER_RANK = int(os.environ.get("RENDERTOY_B200_FRAMES_PER_RANK", "8"))
-ORBIT = 256  # World = rotate(2*pi*k/256, y)  
+ORBIT = 256       # World = rotate(2*pi*k/256, y)  
+SUB = 8           # frames per sub-batch = distinct frame targets a rank cycles through (8 x 33 MB > L2)
+RAY_FRAMES = int(os.environ.get("RENDERTOY_B200_RAY_FRAMES", "512"))     # frames per rank and step
+RAS_FRAMES = int(os.environ.get("RENDERTOY_B200_RAS_FRAMES", "1024"))
+TILE_FRAMES = int(os.environ.get("RENDERTOY_B200_TILE_FRAMES", "256"))   # frames per step (all ranks together) in the tile partition
 
 METRIC_RAY = "Mrays/s closest-hit (dragon, 4K)"
 METRIC_RAS = "Mtris/s raster"
+
+# `config` names the workload and nothing else: both arms (ours, --impl reference) print exactly these dicts
+CONFIG_RAY = {"workload": "configs[3]: dragon100k (synthetic stand-in for the missing dragon.obj, 100000 triangles) raycast 3840x2160, "
+                          "lesson06 camera orbit, primary rays + closest hit + Lambert shade",
+              "triangles": N_TRIS, "width": RAY_W, "height": RAY_H,
+              "camera": "tutorials/lesson06_loading_obj.py:74-83, World = rotate(2*pi*k/256, y), frame k of a 256-frame orbit"}
+CONFIG_RAS = {"workload": "configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders, clear + clear + draw_triangles per frame",
+              "triangles": N_TRIS, "width": RAS_W, "height": RAS_H,
+              "camera": "tutorials/lesson08_rasterization.py:90-99, World = rotate(2*pi*k/256, y), frame k of a 256-frame orbit"}
 
 
 def peaks():
@@ -48,8 +62,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """Per-launch DRAM bytes from the committed ncu --set full captures (profiles/traffic.json), or None."""
+def ncu_fact(name):
+    v = ncu_facts().get(name)
+    if isinstance(v, dict):
+        return v
+    return {} if v is None else {"dram_bytes_per_launch": v}
+
+
+def ncu_facts():
+    """Per-launch facts read off the committed ncu --set full captures (profiles/traffic.json): DRAM bytes, executed warp
+    instructions, issue-slot utilisation.  bench.py never runs under a profiler; these are static properties of the same
+    kernels on the same scene, used to state the binding roofline (instruction issue) next to the HBM one."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
 
@@ -82,40 +105,54 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 # ---------------------------------------------------------------------------------------------------------
-# scene helpers
+# scene / distributed helpers
 # ---------------------------------------------------------------------------------------------------------
 
 def orbit_t(k):
     return 2.0 * math.pi * (k % ORBIT) / ORBIT
 
 
-def make_mesh(ren):
-    from rendertoy_b200 import scenes
-    rows = scenes.dragon(N_TRIS)
+def upload(ren, rows):
     vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
     with ren.mapped(vb) as m:
         m.view(np.float32).reshape(rows.shape)[:] = rows
-    return rows, vb
+    return vb
 
 
-def ray_camera(ren, k):
-    from rendering._raycaster import camera_frame
-    from rendertoy_b200 import scenes
-    world, view, proj = scenes.lesson_camera(ren, 6, orbit_t(k), RAY_W, RAY_H)
-    return camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+_CAMS = {}
 
 
-def dist_setup(n_gpus):
+def ray_camera(ren, k, lesson=6, w=RAY_W, h=RAY_H):
+    """12-float camera frame of orbit frame k (cached: the orbit has 256 distinct frames)."""
+    key = (lesson, k % ORBIT, w, h)
+    if key not in _CAMS:
+        from rendering._raycaster import camera_frame
+        from rendertoy_b200 import scenes
+        world, view, proj = scenes.lesson_camera(ren, lesson, orbit_t(k), w, h)
+        _CAMS[key] = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+    return _CAMS[key]
+
+
+def raster_camera(ren, k, w=RAS_W, h=RAS_H):
+    key = ("ras", k % ORBIT, w, h)
+    if key not in _CAMS:
+        from rendertoy_b200 import scenes
+        _CAMS[key] = scenes.lesson_camera(ren, 8, orbit_t(k), w, h)
+    return _CAMS[key]
+
+
+def dist_setup():
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -133,441 +170,622 @@ def barrier_sync(world):
     torch.cuda.synchronize()
 
 
-def all_ranks(ms, world):
-    """every rank's value, in rank order (for the per-rank breakdown in the JSON line)"""
+def all_ranks(v, world):
+    """every rank's value, in rank order"""
     import torch
     import torch.distributed as dist
     if world > 1:
         t = torch.zeros(world, dtype=torch.float64, device="cuda")
-        t[dist.get_rank()] = ms
+        t[dist.get_rank()] = v
         dist.all_reduce(t)
         return [float(x) for x in t.cpu()]
-    return [ms]
+    return [float(v)]
 
 
 def max_over_ranks(ms, world):
+    return max(all_ranks(ms, world))
+
+
+def all_ok(ok, world):
     import torch
-    import torch.distributed as dist
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-    return ms
+    if world == 1:
+        return bool(ok)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+class Streams:
+    """Independent frames alternate over a few CUDA streams so one frame's tail overlaps its neighbours; forked from / joined
+    into the main stream only where something has to be ordered (timing events, the commit of a gather)."""
+
+    def __init__(self, n):
+        import torch
+        self.torch = torch
+        self.main = torch.cuda.current_stream()
+        self.streams = [torch.cuda.Stream() for _ in range(n)] if n > 1 else []
+
+    def fork(self):
+        for st in self.streams:
+            st.wait_stream(self.main)
+
+    def use(self, i):
+        if self.streams:
+            st = self.streams[i % len(self.streams)]
+            self.torch.cuda.set_stream(st)       # (the `with torch.cuda.stream()` context costs ~15 us of Python)
+            return st
+        return self.main
+
+    def join(self, *extra):
+        if self.streams:
+            self.torch.cuda.set_stream(self.main)
+            for st in self.streams:
+                self.main.wait_stream(st)
+        for st in extra:
+            self.main.wait_stream(st)
 
 
 # ---------------------------------------------------------------------------------------------------------
-# primary: ray casting, configs[3]
+# animation batch (frames k = rank mod N), both paths: the frame loop with its gather
 # ---------------------------------------------------------------------------------------------------------
 
-def bench_raycast(args, rank, world):
+class FrameLoop:
+    """Runs `frames` frames per rank and step through `render(i, k, target_index, in_store_slot) -> content rect`, cycling SUB
+    local targets, and gathers them into rank 0's frame store:
+
+      gather == "copy": ranks != 0 render locally, a copy engine pushes each finished frame's content rect into its slot
+                        (cover_rect: only what can differ from what the slot holds); rank 0 renders in place
+      gather == "peer": every rank's kernels store straight into the slots over NVLink (the render targets ARE the slots)
+      gather == "nccl": render locally, grouped send/recv per sub-batch (baseline)
+
+    The store is a ring of 2 * commit_every sub-batches (SUB frames per rank each); a stream-ordered 4-byte all-reduce every
+    `commit_every` sub-batches tells rank 0 those frames are complete, and a slot is rewritten only two commits later."""
+
+    def __init__(self, ren, world, rank, W, H, frames, gather, commit_every, n_streams, make_target):
+        import torch
+        from rendertoy_b200 import parallel
+        self.torch, self.ren, self.world, self.rank, self.W, self.H, self.frames = torch, ren, world, rank, W, H, frames
+        self.parallel = parallel
+        self.C = max(1, commit_every)
+        self.ring = 2 * self.C                          # sub-batches in the ring
+        assert frames % (SUB * self.C) == 0, "frames per step must be a multiple of SUB * commit_every"
+        self.store = None
+        self.gather = gather if world > 1 else "none"
+        if self.gather in ("copy", "peer"):
+            self.store = parallel.FrameStore(self.ring * SUB * world, W, H)
+            if not self.store.ok:
+                self.gather = "nccl"
+        self.in_store = self.gather == "peer" or (self.gather == "copy" and rank == 0)
+        if self.in_store:      # one target object per slot this rank renders into
+            self.targets = [make_target(self.store.frame(self.slot(q, j))) for q in range(self.ring) for j in range(SUB)]
+        else:
+            self.targets = [make_target(None) for _ in range(SUB)]
+        self.streams = Streams(n_streams)
+        self.push_stream = torch.cuda.Stream() if (self.gather == "copy" and rank != 0) else None
+        self.pushed = [None] * SUB                      # event: the push out of local target j has finished reading it
+        self.rendered_ev = [torch.cuda.Event() for _ in range(SUB)]
+        self.pushed_ev = [torch.cuda.Event() for _ in range(SUB)]
+        self.pushed_bytes = 0
+        self.q = 0                                      # global sub-batch counter
+        if self.gather == "nccl":
+            self.local = torch.empty((SUB, H, W), dtype=torch.int32, device="cuda")
+            self.gathered = torch.empty((SUB * world, H, W), dtype=torch.int32, device="cuda") if rank == 0 else None
+
+    def slot(self, q, j):
+        return ((q % self.ring) * SUB + j) * self.world + self.rank
+
+    def target(self, q, j):
+        return self.targets[(q % self.ring) * SUB + j] if self.in_store else self.targets[j]
+
+    def step(self, s, render, sparse=True):
+        torch = self.torch
+        full = (0, 0, self.W - 1, self.H - 1)
+        self.streams.fork()
+        for b in range(self.frames // SUB):
+            q = self.q
+            for j in range(SUB):
+                i = b * SUB + j
+                k = (s * self.frames + i) * self.world + self.rank          # global frame number -> orbit position
+                st = self.streams.use(i)
+                if self.push_stream is not None and self.pushed[j] is not None:
+                    st.wait_event(self.pushed[j])                              # the target's previous frame has left
+                tgt = self.target(q, j)
+                content = render(i, k, tgt)
+                if self.push_stream is not None:
+                    self.rendered_ev[j].record(st)
+                    self.push_stream.wait_event(self.rendered_ev[j])
+                    self.pushed_bytes += self.store.push(self.slot(q, j), tgt_ptr(tgt), content if sparse else full, self.push_stream.cuda_stream)
+                    self.pushed_ev[j].record(self.push_stream)
+                    self.pushed[j] = self.pushed_ev[j]
+            self.q += 1
+            if self.gather == "nccl":
+                self.streams.join()
+                for j in range(SUB):
+                    self.local[j].copy_(tgt_tensor(self.targets[j]).view(torch.int32).view(self.H, self.W))
+                self.parallel.gather_frames(self.local, self.gathered, SUB * self.world)
+                self.streams.fork()
+            elif self.store is not None and self.q % self.C == 0:
+                self.streams.join(*([self.push_stream] if self.push_stream is not None else []))
+                self.store.commit()
+                self.streams.fork()
+        self.streams.join(*([self.push_stream] if self.push_stream is not None else []))
+
+    def close(self):
+        if self.store is not None:
+            self.torch.cuda.synchronize()
+            barrier_sync(self.world)
+            self.targets = None
+            self.store.close()
+            self.store = None
+
+    def verify_last(self):
+        """Untimed: the slots of the last sub-batch hold exactly what this rank rendered locally (read back over NVLink)."""
+        if self.gather != "copy":
+            return None
+        ok = True
+        if self.rank != 0:
+            q = self.q - 1
+            for j in range(SUB):
+                slot = self.store.frame(self.slot(q, j)).view(self.torch.int32)
+                ok &= bool(self.torch.equal(slot, tgt_tensor(self.targets[j]).view(self.torch.int32).view(-1)))
+        return all_ok(ok, self.world)
+
+
+def tgt_ptr(t):
+    """device address of a frame target: an Image, or a (Raster, globals...) tuple"""
+    return (t[0].get_render_target() if isinstance(t, tuple) else t).ptr
+
+
+def tgt_tensor(t):
+    return (t[0].get_render_target() if isinstance(t, tuple) else t).buffer.tensor()
+
+
+def gather_text(loop, sparse):
+    if loop.world == 1:
+        return "single GPU, no gather"
+    ring = f"frame store = ring of {loop.ring} sub-batches x {SUB} frames per rank, one stream-ordered 4-byte all-reduce per {loop.C} sub-batches"
+    if loop.gather == "peer":
+        return "every rank's kernel stores its pixels straight into rank 0's frame store over NVLink (CUDA IPC peer memory); " + ring
+    if loop.gather == "copy":
+        return ("ranks != 0 render locally and push each finished frame into rank 0's frame store (CUDA IPC peer memory, cleared at start) with an "
+                "async pitched copy-engine transfer that overlaps the next frames" + ("; only the pixel rect that can differ from the slot's content "
+                "travels (union of this frame's and the previous frame's content rect: the frame is the clear colour elsewhere)" if sparse else "")
+                + "; rank 0 renders in place; " + ring)
+    return "framebuffers gathered to rank 0 with NCCL send/recv per sub-batch"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primary: ray casting
+# ---------------------------------------------------------------------------------------------------------
+
+def bench_raycast(args, rank, world, rows, vb, W=RAY_W, H=RAY_H, lesson=6, frames=None, full=True, n_tris=N_TRIS):
+    """full: also e2e, the isolated-launch figure, the instrumented pass and the frame-filling camera (the primary line);
+    otherwise only the device-timed loop (config4)."""
     import torch
     import rendering as ren
     from rendering._raycaster import Raycaster
     from rendertoy_b200 import parallel
-    from rendertoy_b200._native import SHADER_LESSON08
 
-    rows, vb = make_mesh(ren)
+    F = frames or RAY_FRAMES
     rc = Raycaster([ren.Mesh(vb, None)])
-    F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
-    my_frames = parallel.frame_indices(n_frames, rank, world)
-    store = parallel.FrameStore(2 * n_frames, RAY_W, RAY_H) if (world > 1 and args.gather in ("peer", "copy")) else None
-    fused = store is not None and store.ok and args.gather == "peer"
-    pushed = store is not None and store.ok and args.gather == "copy"
-    if pushed:  # ranks != 0 render locally and a copy engine pushes each finished frame into rank 0's frame store while the
-        # next frame traces; rank 0 renders straight into the store
-        slots2 = [[store.frame(b * n_frames + k) for k in my_frames] for b in range(2)]
-        if rank == 0:
-            targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=m) for m in slots2[b]] for b in range(2)]
-            targets = targets2[0]
-        else:
-            targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
-        push_stream = torch.cuda.Stream()
-        push_ptr = push_stream.cuda_stream
-        rendered = [torch.cuda.Event() for _ in range(F)]
-        local_ptrs = [t.ptr for t in targets] if rank != 0 else None
-        local = gathered = None
-    elif fused:   # render targets ARE rank 0's frame store (peer-mapped, double-buffered): the kernel's BGRA8 stores are the gather
-        targets2 = [[ren.Image(RAY_W, RAY_H, ren._core.RGBA, memory=store.frame(b * n_frames + k)) for k in my_frames] for b in range(2)]
-        targets = targets2[0]
-        local = gathered = None
-    else:
-        targets = [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]     # F x 33 MB > L2
-        local = torch.empty((F, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if world > 1 else None
-        gathered = torch.empty((n_frames, RAY_H, RAY_W), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
-    cams = {k: ray_camera(ren, k) for k in range(n_frames * (args.steps + args.warmup))}
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * args.steps)]
+    loop = FrameLoop(ren, world, rank, W, H, F, args.gather, args.commit_every, args.raycast_streams,
+                     lambda mem: ren.Image(W, H, ren._core.RGBA, memory=mem) if mem is not None else ren.create_image2d(W, H, ren._core.RGBA))
+    for k in range(ORBIT):
+        ray_camera(ren, k, lesson, W, H)
 
-    # frames of an orbit are independent: alternating them over a few streams overlaps one frame's tail (and the next
-    # frame's projection pass) with its neighbour; each stream has its own screen-space node scratch inside Raycaster
-    ray_streams = [torch.cuda.Stream() for _ in range(args.raycast_streams)] if args.raycast_streams > 1 else None
-    main_stream = torch.cuda.current_stream()
-
-    def step(s, timed_idx=None):
-        tg = targets2[s % 2] if (fused or (pushed and rank == 0)) else targets
-        if ray_streams is not None:
-            for st in ray_streams:
-                st.wait_stream(main_stream)
-        for j, k in enumerate(my_frames):
-            if ray_streams is not None:
-                torch.cuda.set_stream(ray_streams[j % len(ray_streams)])
-            if timed_idx is not None:
-                ev[timed_idx * F + j][0].record()
-            content = rc.render(tg[j], cams[s * n_frames + k])
-            if timed_idx is not None:
-                ev[timed_idx * F + j][1].record()
-            if pushed and rank != 0:
-                # the frame is the clear colour outside `content` (the scene's projected bounds): only that rect travels
-                rendered[j].record()
-                push_stream.wait_event(rendered[j])
-                pushed_bytes[0] += store.push((s % 2) * n_frames + k, local_ptrs[j], content if args.sparse else full_rect, push_ptr)
-        if ray_streams is not None:
-            torch.cuda.set_stream(main_stream)
-            for st in ray_streams:
-                main_stream.wait_stream(st)
-        if pushed:
-            main_stream.wait_stream(push_stream)
-        collect()
-
-    full_rect = (0, 0, RAY_W - 1, RAY_H - 1)
-    pushed_bytes = [0]
-
-    def collect():   # the only collective: finished frames -> rank 0
-        if fused or pushed:
-            store.commit()
-        elif world > 1:
-            for j in range(F):
-                local[j].copy_(targets[j].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W))
-            parallel.gather_frames(local, gathered, n_frames)
+    def render(i, k, tgt):
+        return rc.render(tgt, ray_camera(ren, k, lesson, W, H))
 
     for s in range(args.warmup):
-        step(s)
+        loop.step(s, render, args.sparse)
     sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
     barrier_sync(world)
-    pushed_bytes[0] = 0
+    loop.pushed_bytes = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        step(args.warmup + s, timed_idx=s)
+        loop.step(args.warmup + s, render, args.sparse)
     e1.record()
     barrier_sync(world)
     clocks = sampler.result()
-    # untimed check of the gather: every rank compares the frames of the last step it rendered locally with what now
-    # sits in its slots of rank 0's frame store (read back over NVLink), bit for bit
-    gather_ok = None
-    if pushed:
-        s_last = args.warmup + args.steps - 1
-        ok = 1
-        if rank != 0:
-            for j, k in enumerate(my_frames):
-                slot = store.frame((s_last % 2) * n_frames + k).view(torch.int32)
-                ok &= int(torch.equal(slot, targets[j].buffer.tensor().view(torch.int32).view(-1)))
-        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-        gather_ok = bool(flag.item())
-        assert gather_ok, "frames in rank 0's frame store differ from the frames the ranks rendered"
-    push_bytes_step = all_ranks(pushed_bytes[0] / max(args.steps, 1), world)
-    ms_ranks = all_ranks(e0.elapsed_time(e1), world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
-    rays_total = RAY_W * RAY_H * n_frames * args.steps
-    value = rays_total / (ms * 1e-3) / 1e6
-    launch_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))   # per frame, on its own stream, inside the timed region
-    # with frames overlapping on several streams a launch's own duration includes its neighbours' share of the GPU:
-    # the duration that explains `value` is the timed region divided by the launches in it
-    kernel_ms = (e0.elapsed_time(e1) / (args.steps * F)) if ray_streams is not None else launch_ms
-    # the same launch pair alone on the GPU (after the timed region)
-    iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F)]
-    for j, k in enumerate(my_frames):
-        iso[j][0].record(); rc.render(targets[j], cams[k]); iso[j][1].record()
-    torch.cuda.synchronize()
-    isolated_ms = float(np.mean([a.elapsed_time(b) for a, b in iso]))
+    gather_ok = loop.verify_last()
+    assert gather_ok is not False, "frames in rank 0's frame store differ from the frames the ranks rendered"
+    ms_local = e0.elapsed_time(e1)
+    ms_ranks = all_ranks(ms_local, world)
+    ms = max(ms_ranks)
+    push_bytes_step = all_ranks(loop.pushed_bytes / max(args.steps, 1), world)
+    value = W * H * F * world * args.steps / (ms * 1e-3) / 1e6
+    kernel_ms = ms_local / (args.steps * F)      # timed region / launch pairs in it (frames overlap on the streams)
+    out = {"value": value, "ms": ms, "ms_ranks": ms_ranks, "kernel_ms": kernel_ms, "clocks": clocks, "frames": F,
+           "gather": gather_text(loop, args.sparse), "gather_verified": gather_ok, "push_bytes_step": push_bytes_step,
+           "launches": (2 + args.view_refit) * F * args.steps, "view_nodes": rc.n_triangles <= 1 << 18}
+    if not full:
+        loop.close()
+        return out
 
-    # instrumented pass (outside the timed region): node visits / triangle tests per ray
-    stats = torch.zeros(3, dtype=torch.int64, device="cuda")
-    rc.render(targets[0], cams[my_frames[0]], stats=stats)
+    targets = loop.targets[:SUB]
+    # the same launch pair alone on the GPU
+    iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(SUB)]
+    for j in range(SUB):
+        iso[j][0].record(); rc.render(targets[j], ray_camera(ren, j * world + rank)); iso[j][1].record()
     torch.cuda.synchronize()
-    nodes, tests, rays = (int(x) for x in stats.cpu())
+    out["kernel_ms_alone"] = float(np.mean([a.elapsed_time(b) for a, b in iso]))
+
+    # instrumented pass: node visits / triangle tests per ray
+    stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+    rc.render(targets[0], ray_camera(ren, rank), stats=stats)
+    torch.cuda.synchronize()
+    out["stats"] = tuple(int(x) for x in stats.cpu())
+
+    # the frame-filling camera (lesson08's, eye at distance 1: the mesh covers ~38 % of the 4K frame, the traced rect ~90 %)
+    streams = Streams(args.raycast_streams)
+    n_ff = 64
+
+    def ff_pass():
+        streams.fork()
+        for i in range(n_ff):
+            streams.use(i)
+            rc.render(targets[i % SUB], ray_camera(ren, i * world + rank, 8))
+        streams.join()
+    ff_pass()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record(); ff_pass(); ff_pass(); f1.record()
+    torch.cuda.synchronize()
+    ff_ms = f0.elapsed_time(f1) / (2 * n_ff)
+    stats.zero_()
+    rc.render(targets[0], ray_camera(ren, rank, 8), stats=stats)
+    torch.cuda.synchronize()
+    ff_stats = tuple(int(x) for x in stats.cpu())
+    out["frame_filling"] = {"camera": "tutorials/lesson08_rasterization.py:90-99 (eye (0,0.3,1)) at 3840x2160, same orbit", "value": W * H / ff_ms / 1e3,
+                            "unit": "Mrays/s", "ms_per_frame": ff_ms, "rays_traced_fraction": ff_stats[2] / (W * H), "n_gpus": 1,
+                            "inner_node_visits_per_ray": ff_stats[0] / (W * H), "triangle_tests_per_ray": ff_stats[1] / (W * H),
+                            "note": "per GPU, no gather; frames alternate over the same streams"}
 
     # ---- e2e: public API, host inputs, every frame read back to pinned host memory
-    host = [torch.zeros((RAY_H, RAY_W), dtype=torch.int32).pin_memory() for _ in range(2)]   # cleared, like the frames
+    host = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]   # cleared, like the frames
     copy_stream = torch.cuda.Stream()
     copy_ptr = copy_stream.cuda_stream
-    done = [torch.cuda.Event() for _ in range(2)]
-    reader = parallel.SparseFrameCopier(RAY_W, RAY_H)
     from rendertoy_b200 import scenes
     from rendering._raycaster import camera_frame
+    # e2e delivers frames to HOST memory: every rank reads its own frames back over its own PCIe link, so the GPU-side
+    # gather is not on this path (local targets, no collective)
+    e2e_targets = [ren.create_image2d(W, H, ren._core.RGBA) for _ in range(SUB)] if (loop.in_store and world > 1) else targets
+    e2e_streams = Streams(2 if args.raycast_streams > 1 else 1)       # measured: 43.6 Grays/s with 2, 40.3 with 1, 38.8 with 4
+    full_rect = (0, 0, W - 1, H - 1)
 
-    # e2e delivers frames to HOST memory: on one node every rank reads its own frames back over its own PCIe link, so
-    # the GPU-side gather to rank 0 is not on this path (local targets, no collective)
-    e2e_targets = targets if not fused else [ren.create_image2d(RAY_W, RAY_H, ren._core.RGBA) for _ in range(F)]
+    rendered = [torch.cuda.Event() for _ in range(SUB)]
+    read_done = [torch.cuda.Event() for _ in range(SUB)]
 
-    # like the device-resident loop, the frames of a batch alternate over streams, but two of them: measured 43.6 Grays/s
-    # with 2, 40.3 with 1, 38.8 with 4, 35.0 with 8 (the renders compete with the copy engine's reads)
-    e2e_streams = ray_streams[:2] if ray_streams is not None else None
-
-    def e2e_step(s):
-        ray_streams = e2e_streams
-        if ray_streams is not None:
-            for st in ray_streams:
-                st.wait_stream(main_stream)
-        for j, k in enumerate(my_frames):
-            world_m, view, proj = scenes.lesson_camera(ren, 6, orbit_t(s * n_frames + k), RAY_W, RAY_H)   # host inputs
+    def e2e_pass(n, s0, reader, sparse):
+        """n frames: host matrices -> camera frame -> render -> async D2H copy into one of two pinned host frames"""
+        e2e_streams.fork()
+        for i in range(n):
+            k = (s0 + i) * world + rank
+            j = i % SUB
+            world_m, view, proj = scenes.lesson_camera(ren, lesson, orbit_t(k), W, H)     # host inputs, computed every frame
             cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world_m, dtype=ren.float4x4))
-            if ray_streams is not None:
-                torch.cuda.set_stream(ray_streams[j % len(ray_streams)])
+            st = e2e_streams.use(i)
+            if i >= SUB:
+                st.wait_event(read_done[j])      # the frame this target held has been read back
             content = rc.render(e2e_targets[j], cam)
-            done[j % 2].record()
-            copy_stream.wait_event(done[j % 2])
-            # the frame is the clear colour outside `content`, and so is the (initially cleared) host frame outside the
-            # content of the frame it held before: one pitched D2H copy of the union makes the host frame complete
-            reader.copy(j % 2, host[j % 2].data_ptr(), e2e_targets[j].ptr, content if args.sparse_readback else full_rect, copy_ptr)
-        if ray_streams is not None:
-            torch.cuda.set_stream(main_stream)
-            for st in ray_streams:
-                main_stream.wait_stream(st)
-        main_stream.wait_stream(copy_stream)
+            rendered[j].record(st)
+            copy_stream.wait_event(rendered[j])
+            reader.copy(i % 2, host[i % 2].data_ptr(), e2e_targets[j].ptr, content if sparse else full_rect, copy_ptr)
+            read_done[j].record(copy_stream)
+        e2e_streams.join(copy_stream)
 
-    e2e_step(0)
-    barrier_sync(world)
+    def e2e_measure(n_frames, sparse):
+        reader = parallel.SparseFrameCopier(W, H)
+        for hbuf in host:
+            hbuf.zero_()
+        e2e_pass(2 * SUB, 0, reader, sparse)
+        barrier_sync(world)
+        reader.bytes_moved = 0
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        e2e_pass(n_frames, 2 * SUB, reader, sparse)
+        g1.record()
+        barrier_sync(world)
+        ms_e = max_over_ranks(g0.elapsed_time(g1), world)
+        j_last = (n_frames - 1) % SUB
+        ok = bool(torch.equal(host[(n_frames - 1) % 2], e2e_targets[j_last].buffer.tensor().view(torch.int32).view(H, W).cpu()))
+        assert ok, "read-back: the host frame differs from the device frame"
+        return W * H * n_frames * world / (ms_e * 1e-3) / 1e6, reader.bytes_moved, ok, ms_e
+
     k_e2e = max(2, min(args.steps, 5))
-    reader.bytes_moved = 0
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for s in range(k_e2e):
-        e2e_step(1 + s)
-    g1.record()
-    barrier_sync(world)
-    e2e_ms = max_over_ranks(g0.elapsed_time(g1), world)
-    # untimed check: the host frame that received the last frame is that frame, every pixel
-    j_last = F - 1
-    e2e_ok = bool(torch.equal(host[j_last % 2], e2e_targets[j_last].buffer.tensor().view(torch.int32).view(RAY_H, RAY_W).cpu()))
-    assert e2e_ok, "sparse read-back: the host frame differs from the device frame"
-    e2e_value = RAY_W * RAY_H * n_frames * k_e2e / (e2e_ms * 1e-3) / 1e6
-
-    hbm_peak, peak_src = peaks()
-    alg_bytes = 12 * RAY_W * RAY_H + N_TRIS * 96 + (2 * N_TRIS - 1) * 32          # SURVEY.md section 8(d)
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    sm_count = torch.cuda.get_device_properties(0).multi_processor_count
-    fp32_peak = sm_count * 128 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
-    flops = nodes * 10 + tests * 45              # totals of one full instrumented frame (culled pixels trace nothing)
-    out = {
-        "metric": METRIC_RAY, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[3]: dragon100k (synthetic stand-in for the missing dragon.obj, 100000 triangles) "
-                               "raycast 3840x2160, lesson06 camera orbit, primary rays + closest hit + Lambert shade",
-                   "frames_per_rank_per_step": F,
-                   "partition": "frames k = rank (mod N); " + ("every rank's kernel stores its pixels straight into rank 0's frame store "
-                                "over NVLink (CUDA IPC peer memory, double-buffered), one stream-ordered 4-byte all-reduce per step" if fused else
-                                "ranks != 0 render locally and push each finished frame into rank 0's frame store (CUDA IPC peer memory, "
-                                "double-buffered, cleared at start) with an async pitched copy-engine transfer that overlaps the next frame"
-                                + ("; only the pixel rect that can differ from the slot's content travels (union of the scene's projected "
-                                   "bounds of this frame and of the slot's previous frame: the frame is the clear colour elsewhere)" if args.sparse else "")
-                                + "; rank 0 renders in place; one stream-ordered 4-byte all-reduce per step" if pushed else
-                                "framebuffers gathered to rank 0 with NCCL send/recv" if world > 1 else "single GPU, no gather"),
-                   "l2": "each rank cycles 8 distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay "
-                         "L2-resident by design, as they are reused every frame",
-                   "streams": f"frames alternate over {args.raycast_streams} CUDA streams" if ray_streams else "single stream",
-                   "bvh_build_excluded": True, "timed_region_ms_per_rank": ms_ranks,
-                   **({"gather_verified": "every rank's locally rendered frames of the last step == its slots of rank 0's frame store, bit for bit",
-                       "gather_bytes_per_step_per_rank": push_bytes_step, "full_frame_bytes_per_step_per_rank": 4 * RAY_W * RAY_H * F}
-                      if gather_ok else {})},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic().get("raycast_kernel"), "peak_source": peak_src,
-                     "kernel": "raycast_kernel<8> (+ project_kernel, same launch pair)", "kernel_ms": kernel_ms, "kernel_ms_alone": isolated_ms, "kernel_ms_overlapped_launch": launch_ms,
-                     "kernel_ms_note": "kernel_ms = timed region / launches in it (frames overlap on the streams named in config); "
-                                       "kernel_ms_alone = one frame's launch pair with nothing else on the GPU; "
-                                       "kernel_ms_overlapped_launch = CUDA events around each launch pair inside the timed region",
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "HBM does not bind this kernel (BVH and its per-frame screen-space copy are L2-resident); the binding "
-                             "unit is the instruction issue rate (compares, votes, branches of the packet walk: ~73 % of issue "
-                             "slots busy in profiles/), see fp32 for the arithmetic it amounts to",
-                     "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
-                              "inner_node_visits_per_ray": nodes / (RAY_W * RAY_H), "triangle_tests_per_ray": tests / (RAY_W * RAY_H),
-                              "rays_traced_fraction": rays / (RAY_W * RAY_H),
-                              "flop_model": "per voting lane: 10 float compares per inner node (two screen rectangles + depth bound "
-                                            "each) + 45 flop per Moller-Trumbore test; peak counts FMA as 2 flop, this kernel is "
-                                            "compiled -fmad=false for bit-exact parity"}},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": reader.bytes_moved // k_e2e,
-                "frame_bytes_per_step": 4 * RAY_W * RAY_H * F, "readback_verified": e2e_ok,
-                "steps": k_e2e, "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async pitched D2H copy into a "
-                                        "pinned, initially cleared host frame" + (" of the pixel rect that can differ from the clear colour (union "
-                                        "of the scene's projected bounds of this frame and of the frame the host buffer held before); the host "
-                                        "frame is complete and checked against the device frame after the timed region" if args.sparse_readback
-                                        else " of the whole 33 MB frame") + "; every rank reads back its own frames"},
-        "gpu_launches": (2 + args.view_refit) * F * args.steps, "clocks": clocks,   # project_kernel (+ experimental refit passes) + raycast kernel per frame
-    }
-    return out, rows
+    n_e2e = k_e2e * F
+    e2e_value, e2e_bytes, e2e_ok, e2e_ms = e2e_measure(n_e2e, args.sparse_readback)
+    dense_value, dense_bytes, _, dense_ms = e2e_measure(max(SUB * 8, n_e2e // 8), False)
+    out["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": e2e_bytes // k_e2e,
+                  "frame_bytes_per_step": 4 * W * H * F, "readback_verified": e2e_ok, "steps": k_e2e, "timed_region_ms": e2e_ms,
+                  "dense_readback": {"value": dense_value, "unit": "Mrays/s", "d2h_bytes_per_frame": 4 * W * H, "timed_region_ms": dense_ms,
+                                     "note": "the same loop reading every frame back whole (33 MB per frame over PCIe)"},
+                  "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async pitched D2H copy into a pinned, initially cleared "
+                          "host frame" + (" of the pixel rect that can differ from the clear colour (union of the scene's projected bounds of this "
+                          "frame and of the frame the host buffer held before); the host frame is complete and checked against the device frame "
+                          "after the timed region" if args.sparse_readback else " of the whole 33 MB frame") + "; every rank reads back its own frames"}
+    del targets, e2e_targets
+    loop.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
-# secondary: rasterization, configs[1]
+# secondary: rasterization
 # ---------------------------------------------------------------------------------------------------------
 
-def bench_raster(args, rank, world, rows=None):
+def bench_raster(args, rank, world, rows, vb, W=RAS_W, H=RAS_H, frames=None, full=True, n_tris=N_TRIS):
     import torch
     import rendering as ren
-    from rendertoy_b200 import lessons, scenes, parallel
+    from rendertoy_b200 import lessons, parallel
 
-    if rows is None:
-        rows, vb = make_mesh(ren)
-    else:
-        vb = ren.create_buffer(rows.shape[0], ren.MeshVertex)
-        with ren.mapped(vb) as m:
-            m.view(np.float32).reshape(rows.shape)[:] = rows
-    F, n_frames = FRAMES_PER_RANK, FRAMES_PER_RANK * world
-    my_frames = parallel.frame_indices(n_frames, rank, world)
-    # F independent targets (key 16.6 MB + colour 8.3 MB + records 12.8 MB each: ~300 MB > L2)
-    store = parallel.FrameStore(2 * n_frames, RAS_W, RAS_H) if (world > 1 and args.gather != "nccl") else None
-    # --raster-gather copy (EXPERIMENTAL, not yet measured): as for the ray-cast frames, ranks != 0 render locally and a copy engine
-    # pushes Raster.content_rect into rank 0's frame store; rank 0 renders in place.  Default: every rank's kernels store into the store.
-    ras_push = store is not None and store.ok and args.raster_gather == "copy"
-    fused = store is not None and store.ok and not ras_push
-    in_store = fused or (ras_push and rank == 0)         # this rank's render targets are slots of the store
-    rasters, rasters_b = [], []
-    for j in range(F):
-        target = ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(my_frames[j])) if in_store else \
-            ren.create_presenter(RAS_W, RAS_H).get_render_target()
-        rasters.append(lessons.build_lesson08(ren, target))
-        if in_store:   # second half of the double-buffered frame store
-            rasters_b.append(lessons.build_lesson08(ren, ren.Image(RAS_W, RAS_H, ren._core.RGBA, memory=store.frame(n_frames + my_frames[j]))))
-    if ras_push:
-        push_stream = torch.cuda.Stream()
-        push_ptr = push_stream.cuda_stream
-        drawn = [torch.cuda.Event() for _ in range(F)]
-    nccl_gather = world > 1 and not fused and not ras_push
-    local = torch.empty((F, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if nccl_gather else None
-    gathered = torch.empty((n_frames, RAS_H, RAS_W), dtype=torch.int32, device="cuda") if (rank == 0 and nccl_gather) else None
-    cams = {k: scenes.lesson_camera(ren, 8, orbit_t(k), RAS_W, RAS_H) for k in range(n_frames * (args.steps + args.warmup + 6))}
+    F = frames or RAS_FRAMES
 
-    # frames of an animation batch are independent: each of the F targets gets its own CUDA stream, so the short
-    # dependent kernel chains of different frames overlap and fill the SMs a single 100k-triangle frame leaves idle
-    streams = [torch.cuda.Stream() for _ in range(F)] if args.raster_streams else None
-    main_stream = torch.cuda.current_stream()
+    def make_target(mem):
+        img = ren.Image(W, H, ren._core.RGBA, memory=mem) if mem is not None else ren.create_presenter(W, H).get_render_target()
+        return lessons.build_lesson08(ren, img)          # (raster, globals)
 
-    def frame(j, k, odd=False):
-        raster, g = rasters_b[j] if (odd and in_store) else rasters[j]
-        if streams is not None:
-            torch.cuda.set_stream(streams[j])          # (the `with torch.cuda.stream()` context costs ~15 us of Python)
-        lessons.set_transforms(ren, g, *cams[k])
+    loop = FrameLoop(ren, world, rank, W, H, F, args.raster_gather, args.commit_every, SUB if args.raster_streams else 1, make_target)
+    for k in range(ORBIT):
+        raster_camera(ren, k, W, H)
+
+    def render(i, k, tgt):
+        raster, g = tgt
+        lessons.set_transforms(ren, g, *raster_camera(ren, k, W, H))
         lessons.render_frame(ren, raster, vb)
-        if ras_push and rank != 0:
-            drawn[j].record()
-            push_stream.wait_event(drawn[j])
-            store.push((n_frames if odd else 0) + my_frames[j], raster.get_render_target().ptr, raster.content_rect, push_ptr)
-        if streams is not None:
-            torch.cuda.set_stream(main_stream)
-
-    def fork():
-        if streams is not None:
-            for st in streams:
-                st.wait_stream(main_stream)
-
-    def join():
-        if streams is not None:
-            for st in streams:
-                main_stream.wait_stream(st)
-        if ras_push:
-            main_stream.wait_stream(push_stream)
-
-    def gather():
-        if fused or ras_push:
-            store.commit()
-        elif world > 1:
-            for j in range(F):
-                local[j].copy_(rasters[j][0].get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W))
-            parallel.gather_frames(local, gathered, n_frames)
-
-    def step(s):
-        fork()
-        for j, k in enumerate(my_frames):
-            frame(j, s * n_frames + k, odd=bool(s & 1))
-        join()
-        gather()
+        return raster.content_rect if loop.push_stream is not None else None
 
     for s in range(args.warmup):
-        step(s)
+        loop.step(s, render, args.sparse)
     barrier_sync(world)
+    loop.pushed_bytes = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        step(args.warmup + s)
+        loop.step(args.warmup + s, render, args.sparse)
     e1.record()
     barrier_sync(world)
-    if ras_push:   # untimed check, as for the ray-cast frames: the slots of the last step hold exactly what this rank rendered
-        odd_last = bool((args.warmup + args.steps - 1) & 1)
-        okf = 1
-        if rank != 0:
-            for j in range(F):
-                slot = store.frame((n_frames if odd_last else 0) + my_frames[j]).view(torch.int32)
-                okf &= int(torch.equal(slot, rasters[j][0].get_render_target().buffer.tensor().view(torch.int32).view(-1)))
-        flag = torch.tensor([okf], dtype=torch.int32, device="cuda")
-        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-        assert bool(flag.item()), "raster frames in rank 0's frame store differ from the frames the ranks rendered"
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
-    tris_total = N_TRIS * n_frames * args.steps
-    value = tris_total / (ms * 1e-3) / 1e6
-    frame_ms = ms / (args.steps * F)
+    gather_ok = loop.verify_last()
+    assert gather_ok is not False, "raster frames in rank 0's frame store differ from the frames the ranks rendered"
+    ms_ranks = all_ranks(e0.elapsed_time(e1), world)
+    ms = max(ms_ranks)
+    value = n_tris * F * world * args.steps / (ms * 1e-3) / 1e6
+    frame_ms = e0.elapsed_time(e1) / (args.steps * F)
+    out = {"value": value, "ms": ms, "ms_ranks": ms_ranks, "frame_ms": frame_ms, "frames": F, "gather": gather_text(loop, args.sparse),
+           "gather_verified": gather_ok, "launches": 4 * F * args.steps, "streams": max(1, len(loop.streams.streams))}
+    if not full:
+        loop.close()
+        return out
 
-    host = [torch.zeros((RAS_H, RAS_W), dtype=torch.int32).pin_memory() for _ in range(2)]   # cleared, like the frames
+    # one frame alone on the GPU
+    raster0, g0_ = loop.targets[0]
+    iso = []
+    for j in range(8):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lessons.set_transforms(ren, g0_, *raster_camera(ren, j, W, H))
+        a.record(); lessons.render_frame(ren, raster0, vb); b.record()
+        iso.append((a, b))
+    torch.cuda.synchronize()
+    out["frame_ms_alone"] = float(np.mean([a.elapsed_time(b) for a, b in iso]))
+
+    # ---- e2e
+    from rendertoy_b200 import scenes
+    host = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     copy_ptr = copy_stream.cuda_stream
-    done = [torch.cuda.Event() for _ in range(2)]
-    reader = parallel.SparseFrameCopier(RAS_W, RAS_H)
-    full_rect = (0, 0, RAS_W - 1, RAS_H - 1)
+    full_rect = (0, 0, W - 1, H - 1)
+    e2e_rasters = [make_target(None) for _ in range(SUB)] if (loop.in_store and world > 1) else loop.targets[:SUB]
 
-    e2e_rasters = rasters if not fused else [lessons.build_lesson08(ren, ren.create_presenter(RAS_W, RAS_H).get_render_target())
-                                             for _ in range(F)]
+    rendered = [torch.cuda.Event() for _ in range(SUB)]
+    read_done = [torch.cuda.Event() for _ in range(SUB)]
 
-    def e2e_step(s):
-        for j, k in enumerate(my_frames):
+    def e2e_pass(n, s0, reader):
+        main = torch.cuda.current_stream()
+        for i in range(n):
+            k = (s0 + i) * world + rank
+            j = i % SUB
             raster, g = e2e_rasters[j]
-            cam = scenes.lesson_camera(ren, 8, orbit_t(s * n_frames + k), RAS_W, RAS_H)      # host matrices every frame
+            cam = scenes.lesson_camera(ren, 8, orbit_t(k), W, H)      # host matrices every frame
             lessons.set_transforms(ren, g, *cam)
+            if i >= SUB:
+                main.wait_event(read_done[j])    # the frame this target held has been read back
             lessons.render_frame(ren, raster, vb)
-            done[j % 2].record()
-            copy_stream.wait_event(done[j % 2])
-            # the frame is the clear colour outside Raster.content_rect (the projected bounding box of what was drawn), and so
-            # is the initially cleared host frame outside the content it held before: one pitched D2H copy of the union
-            reader.copy(j % 2, host[j % 2].data_ptr(), raster.get_render_target().ptr,
+            rendered[j].record(main)
+            copy_stream.wait_event(rendered[j])
+            reader.copy(i % 2, host[i % 2].data_ptr(), raster.get_render_target().ptr,
                         raster.content_rect if args.sparse_readback else full_rect, copy_ptr)
-        torch.cuda.current_stream().wait_stream(copy_stream)
+            read_done[j].record(copy_stream)
+        main.wait_stream(copy_stream)
 
-    e2e_step(args.steps + args.warmup)
+    reader = parallel.SparseFrameCopier(W, H)
+    e2e_pass(2 * SUB, 0, reader)
     barrier_sync(world)
     k_e2e = max(2, min(args.steps, 5))
+    n_e2e = k_e2e * F
     reader.bytes_moved = 0
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for s in range(k_e2e):
-        e2e_step(args.steps + args.warmup + 1 + s)
+    e2e_pass(n_e2e, 2 * SUB, reader)
     g1.record()
     barrier_sync(world)
     e2e_ms = max_over_ranks(g0.elapsed_time(g1), world)
-    last = e2e_rasters[F - 1][0].get_render_target().buffer.tensor().view(torch.int32).view(RAS_H, RAS_W).cpu()
-    e2e_ok = bool(torch.equal(host[(F - 1) % 2], last))
-    assert e2e_ok, "sparse read-back: the host frame differs from the device frame"
-    hbm_peak, peak_src = peaks()
-    alg_bytes = 3 * N_TRIS * 32 + RAS_W * RAS_H * 20                               # SURVEY.md section 8(d), per frame
-    achieved = alg_bytes / (frame_ms * 1e-3) / 1e9
-    return {
-        "metric": METRIC_RAS, "value": value, "unit": "Mtris/s", "ms_per_step": ms / args.steps,
-        "config": {"workload": "configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders, clear + clear + draw_triangles per frame",
-                   "frames_per_rank_per_step": F, "l2": "8 independent raster targets per rank (~300 MB of key/colour/record buffers > L2)",
-                   "streams": "one CUDA stream per frame target (frames of a batch are independent)" if streams else "single stream",
-                   **({"gather": "EXPERIMENTAL copy-engine push of Raster.content_rect, verified against the local frames"} if ras_push else {})},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic().get("raster_frame"), "peak_source": peak_src, "unit_of_work": "one frame = 5 kernels "
-                     "(2 clears, raster_kernel, coverage_kernel, resolve_kernel); algorithmic bytes are defined per frame",
-                     "frame_ms": frame_ms, "algorithmic_bytes_per_frame": alg_bytes},
-        "e2e": {"value": N_TRIS * n_frames * k_e2e / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": 192 * F,
-                "d2h_bytes_per_step": reader.bytes_moved // k_e2e, "frame_bytes_per_step": 4 * RAS_W * RAS_H * F,
-                "readback_verified": e2e_ok, "steps": k_e2e,
-                "note": "per frame: host matrices -> mapped(globals) -> clear, clear, draw_triangles -> async pitched D2H copy into a pinned, "
-                        "initially cleared host frame" + (" of Raster.content_rect (projected bounding box of the drawn mesh, united with "
-                        "the rect of the frame the host buffer held before)" if args.sparse_readback else " of the whole frame")},
-        "gpu_launches": 5 * F * args.steps,
-    }
+    last = e2e_rasters[(n_e2e - 1) % SUB][0].get_render_target().buffer.tensor().view(torch.int32).view(H, W).cpu()
+    e2e_ok = bool(torch.equal(host[(n_e2e - 1) % 2], last))
+    assert e2e_ok, "read-back: the host frame differs from the device frame"
+    out["e2e"] = {"value": n_tris * n_e2e * world / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": 192 * F,
+                  "d2h_bytes_per_step": reader.bytes_moved // k_e2e, "frame_bytes_per_step": 4 * W * H * F,
+                  "readback_verified": e2e_ok, "steps": k_e2e, "timed_region_ms": e2e_ms,
+                  "note": "per frame: host matrices -> mapped(globals) -> clear, clear, draw_triangles -> async pitched D2H copy into a pinned, "
+                          "initially cleared host frame" + (" of Raster.content_rect (projected bounding box of the drawn mesh, united with the rect "
+                          "of the frame the host buffer held before)" if args.sparse_readback else " of the whole frame")}
+    del e2e_rasters, raster0, g0_
+    loop.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs[3] as written: ONE frame split over the ranks by image-space stripes (strong scaling), both paths
+# ---------------------------------------------------------------------------------------------------------
+
+def bench_tiles(args, rank, world, rows, vb):
+    """Every frame is rendered by ALL ranks: rank r owns the row stripes s = r (mod N) of parallel.BAND rows and renders them with one
+    launch (ray cast: rt_raycast_primary(stripes); raster: a scissored draw of the whole mesh) -- into rank 0's frame directly
+    (peer stores) or locally followed by ONE 3-D copy-engine push of its stripes.  value = W*H*frames/t resp. T*frames/t."""
+    import torch
+    import rendering as ren
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200 import lessons, parallel
+
+    C = max(1, args.commit_every)
+    ring = 2 * C * SUB                                  # frames in the ring
+    FT = TILE_FRAMES
+    assert FT % (C * SUB) == 0
+    res = {}
+    for path in ("raycast", "raster"):
+        W, H = (RAY_W, RAY_H) if path == "raycast" else (RAS_W, RAS_H)
+        gather = args.tiles_gather if world > 1 else "none"
+        store = parallel.FrameStore(ring, W, H) if world > 1 else None
+        if store is not None and not store.ok:
+            raise SystemExit("tile partition needs the IPC frame store")
+        stripes = (parallel.BAND, world, rank) if world > 1 else None
+        in_store = store is not None and (gather == "peer" or rank == 0)
+        push_stream = torch.cuda.Stream() if (gather == "copy" and rank != 0) else None
+        n_targets = ring if in_store else SUB
+
+        def image(i):
+            return ren.Image(W, H, ren._core.RGBA, memory=store.frame(i)) if in_store else ren.create_image2d(W, H, ren._core.RGBA)
+        if path == "raycast":
+            rc = Raycaster([ren.Mesh(vb, None)])
+            targets = [image(i) for i in range(n_targets)]
+            streams = Streams(args.raycast_streams)
+
+            def render(f, tgt):
+                return rc.render(tgt, ray_camera(ren, f), stripes=stripes)
+        else:
+            targets = []
+            for i in range(n_targets):
+                raster, g = lessons.build_lesson08(ren, image(i))
+                if stripes is not None:
+                    raster.set_scissor(stripes=stripes)
+                targets.append((raster, g))
+            streams = Streams(SUB if args.raster_streams else 1)
+
+            def render(f, tgt):
+                raster, g = tgt
+                lessons.set_transforms(ren, g, *raster_camera(ren, f))
+                lessons.render_frame(ren, raster, vb)
+                return raster.content_rect if push_stream is not None else None
+        pushed = [None] * SUB
+        counter = [0]
+
+        def step():
+            streams.fork()
+            for _ in range(FT):
+                f = counter[0]
+                st = streams.use(f)
+                j = f % SUB
+                if push_stream is not None and pushed[j] is not None:
+                    st.wait_event(pushed[j])
+                tgt = targets[f % ring] if in_store else targets[j]
+                content = render(f, tgt)
+                if push_stream is not None:
+                    ev = torch.cuda.Event(); ev.record(st)
+                    push_stream.wait_event(ev)
+                    store.push_stripes(f % ring, tgt_ptr(tgt), content, stripes, push_stream.cuda_stream)
+                    done = torch.cuda.Event(); done.record(push_stream)
+                    pushed[j] = done
+                counter[0] += 1
+                if store is not None and counter[0] % (C * SUB) == 0:
+                    streams.join(*([push_stream] if push_stream is not None else []))
+                    store.commit()
+                    streams.fork()
+            streams.join(*([push_stream] if push_stream is not None else []))
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            step()
+        barrier_sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier_sync(world)
+        ms_ranks = all_ranks(e0.elapsed_time(e1), world)
+        ms = max(ms_ranks)
+        # untimed check on rank 0: the gathered frame of the last step equals a whole-frame render of the same camera
+        ok = True
+        if world > 1:
+            f_last = counter[0] - 1
+            if rank == 0:
+                if path == "raycast":
+                    ref = ren.create_image2d(W, H, ren._core.RGBA)
+                    rc.render(ref, ray_camera(ren, f_last))
+                    ref_t = ref.buffer.tensor()
+                else:
+                    raster, g = lessons.build_lesson08(ren, ren.create_image2d(W, H, ren._core.RGBA))
+                    lessons.set_transforms(ren, g, *raster_camera(ren, f_last))
+                    lessons.render_frame(ren, raster, vb)
+                    ref_t = raster.get_render_target().buffer.tensor()
+                torch.cuda.synchronize()
+                ok = bool(torch.equal(store.frame(f_last % ring), ref_t))
+            ok = all_ok(ok, world)
+            assert ok, f"tile partition ({path}): the gathered frame differs from the whole-frame render"
+        units = (W * H) if path == "raycast" else N_TRIS
+        res[path] = {"metric": METRIC_RAY if path == "raycast" else METRIC_RAS, "unit": "Mrays/s" if path == "raycast" else "Mtris/s",
+                     "value": units * FT * args.steps / (ms * 1e-3) / 1e6, "scaling": "strong", "n_gpus": world,
+                     "ms_per_frame": ms / (FT * args.steps), "frames_per_step": FT, "timed_region_ms_per_rank": ms_ranks,
+                     "gathered_frame_verified": ok if world > 1 else None,
+                     "partition": ("single GPU: the whole frame, no stripes" if world == 1 else
+                                   f"every frame split into row stripes of {parallel.BAND} rows, stripe s -> rank s % {world}; one launch per rank and frame; "
+                                   + ("kernels store their stripes straight into rank 0's frame (peer memory)" if gather == "peer" else
+                                      "ranks != 0 render locally and push their stripes with one 3-D copy-engine transfer (content rect only), rank 0 in place")
+                                   + f"; commit (4-byte all-reduce) every {C * SUB} frames")}
+        del targets
+        if store is not None:
+            torch.cuda.synchronize()
+            barrier_sync(world)
+            store.close()
+    res["note"] = ("configs[3] as BASELINE.json words it (image-space tiles of one 4K frame over N GPUs + gather), beside the frames partition of the "
+                   "primary line.  What does not shrink with N: the per-frame projection of the BVH (ray cast) resp. vertex shading + setup of all "
+                   "triangles (raster) are replicated on every rank, plus one launch sequence per rank and frame.")
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs[4]: 10M-triangle instanced scene, 256-frame orbit, 1080p, raster + ray cast, frames k = rank (mod N)
+# ---------------------------------------------------------------------------------------------------------
+
+def bench_config4(args, rank, world, base_rows):
+    import torch
+    import rendering as ren
+    from rendertoy_b200 import scenes
+    t0 = time.perf_counter()
+    vb = scenes.instanced_device(ren, base_rows, grid=10, scale=0.1, seed=1)
+    n_tris = vb.shape[0] // 3
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    W, H = RAS_W, RAS_H
+    per_rank = max(SUB * max(1, args.commit_every), (ORBIT // world) // (SUB * max(1, args.commit_every)) * SUB * max(1, args.commit_every))
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup = max(2, min(args.steps, 4)), 1
+    ras = bench_raster(sub, rank, world, None, vb, W, H, frames=per_rank, full=False, n_tris=n_tris)
+    ray = bench_raycast(sub, rank, world, None, vb, W, H, lesson=8, frames=per_rank, full=False, n_tris=n_tris)
+    hbm, src = peaks()
+    ras_bytes = 3 * n_tris * 32 + W * H * 20
+    ray_bytes = 4 * W * H + n_tris * 96 + (2 * n_tris - 1) * 32
+    return {"workload": "configs[4]: synthetic 10M-triangle instanced dragon scene (10x10 instances of dragon100k, flattened), 256-frame orbit, "
+                        "1920x1080, lesson08 camera, raster + ray cast, frames k = rank (mod N), gathered to rank 0",
+            "triangles": n_tris, "n_gpus": world, "frames_per_rank_per_step": per_rank, "steps": sub.steps, "scene_generation_s": gen_s,
+            "raster": {"value": ras["value"], "unit": "Mtris/s", "ms_per_frame_per_rank": ras["frame_ms"], "timed_region_ms_per_rank": ras["ms_ranks"],
+                       "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": ras_bytes, "achieved": ras_bytes / (ras["frame_ms"] * 1e-3) / 1e9,
+                                    "peak": hbm, "unit": "GB/s", "frac": ras_bytes / (ras["frame_ms"] * 1e-3) / 1e9 / hbm, "peak_source": src},
+                       "gather": ras["gather"]},
+            "raycast": {"value": ray["value"], "unit": "Mrays/s", "ms_per_frame_per_rank": ray["kernel_ms"], "timed_region_ms_per_rank": ray["ms_ranks"],
+                        "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": ray_bytes, "achieved": ray_bytes / (ray["kernel_ms"] * 1e-3) / 1e9,
+                                     "peak": hbm, "unit": "GB/s", "frac": ray_bytes / (ray["kernel_ms"] * 1e-3) / 1e9 / hbm, "peak_source": src,
+                                     "note": "scene (nodes + leaves, 1.6 GB) > L2: every frame streams what its rays touch; an upper bound on the "
+                                             "compulsory bytes, most rays touch a small part of the tree"},
+                        "gather": ray["gather"], "traversal": "per-lane 3-D walk (above 2^18 triangles the screen-space projection pass costs more than it saves)"}}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -575,6 +793,13 @@ def bench_raster(args, rank, world, rows=None):
 # ---------------------------------------------------------------------------------------------------------
 
 _CPU_BVH = {}
+
+
+def cpu_threads():
+    """All host cores, explicitly: torchrun hands its workers OMP_NUM_THREADS=1."""
+    import oracle
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return oracle.set_threads(n)
 
 
 def cpu_raycast(rows, n_frames, first=0, min_seconds=0.0):
@@ -616,7 +841,7 @@ def cpu_raster(rows, n_frames, first=0, min_seconds=0.0):
 
 
 def reference_arm(args):
-    """Times the CPU oracle on this box's host cores, same metric/config as our arm."""
+    """Times the CPU oracle on this box's host cores: same metric, unit and `config` as our arm, one frame per step."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -624,31 +849,111 @@ def reference_arm(args):
     from rendertoy_b200 import scenes
     oracle.build()
     rows = scenes.dragon(N_TRIS)
-    cores = oracle.num_threads()
-    fn, metric, unit, sample = (cpu_raster, METRIC_RAS, "Mtris/s", "1 frame of 1920x1080 x 100000 triangles per step") \
-        if args.path == "raster" else (cpu_raycast, METRIC_RAY, "Mrays/s", "1 frame of 3840x2160 (8.29 Mrays) per step")
+    cores = cpu_threads()
+    if args.path == "raster":
+        fn, metric, unit, units, config = cpu_raster, METRIC_RAS, "Mtris/s", N_TRIS, CONFIG_RAS
+        sample = "1 frame of 1920x1080 x 100000 triangles per step (the orbit's frame k = step)"
+        kind_note = "oracle port of the reference pipeline (rendering/_raster.py kernels restated in C + OpenMP; pyopencl is not installable here)"
+    else:
+        fn, metric, unit, units, config = cpu_raycast, METRIC_RAY, "Mrays/s", RAY_W * RAY_H, CONFIG_RAY
+        sample = "1 frame of 3840x2160 (8.29 Mrays) per step (the orbit's frame k = step)"
+        kind_note = "CPU BVH of oracle/raycast_oracle.c: the reference has NO ray caster (rendering/_raycaster.py:35-36 is `pass`)"
     fn(rows, 1, 0)   # builds the CPU BVH (excluded, as on the GPU side) and faults everything in
     for s in range(args.warmup):
         fn(rows, 1, s)
     t0 = time.perf_counter()
     vals = [fn(rows, 1, args.warmup + s)[0] for s in range(args.steps)]
     wall = time.perf_counter() - t0
-    units = (RAY_W * RAY_H if args.path != "raster" else N_TRIS) * args.steps
-    value = units / wall / 1e6
-    kind_note = ("oracle port of the reference pipeline (rendering/_raster.py kernels restated in C + OpenMP; pyopencl is not installable here)"
-                 if args.path == "raster" else
-                 "CPU BVH of oracle/raycast_oracle.c: the reference has NO ray caster (rendering/_raycaster.py:35-36 is `pass`)")
+    value = units * args.steps / wall / 1e6
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("configs[1]: dragon100k rasterization 1920x1080, lesson08 shaders" if args.path == "raster" else
-                                "configs[3]: dragon100k raycast 3840x2160, lesson06 camera orbit, closest hit + Lambert shade"),
-                   "note": kind_note},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "run": {"note": kind_note, "frames_per_step": 1, "omp_threads": cores, "per_step": vals},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "per_step": vals,
     }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+
+def assemble_ray(args, world, r):
+    hbm_peak, peak_src = peaks()
+    facts = ncu_fact("raycast_frame") or ncu_fact("raycast_kernel")
+    W, H = RAY_W, RAY_H
+    alg_bytes = 4 * W * H + N_TRIS * 96 + (2 * N_TRIS - 1) * 32     # what the timed launch pair moves: BGRA8 out + the scene once (SURVEY.md 8d less the id/t planes the timed call does not write)
+    kernel_ms = r["kernel_ms"]
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    import torch
+    sm_count = torch.cuda.get_device_properties(0).multi_processor_count
+    clock_hz = (r["clocks"]["sm_max_mhz"] or 1965) * 1e6
+    fp32_peak = sm_count * 128 * 2 * clock_hz / 1e12
+    nodes, tests, rays = r["stats"]
+    flops = nodes * 10 + tests * 45
+    issue_peak = sm_count * 4 * clock_hz                      # warp instructions per second: one per scheduler and cycle
+    winstr = facts.get("warp_instructions_per_frame")
+    issue = None
+    if winstr:
+        issue = {"bound": "issue", "warp_instructions_per_frame": winstr, "achieved": winstr / (kernel_ms * 1e-3) / 1e9, "peak": issue_peak / 1e9,
+                 "unit": "G warp-instr/s", "frac": winstr / (kernel_ms * 1e-3) / issue_peak,
+                 "issue_slots_busy_pct_ncu": facts.get("issue_slots_busy_pct"), "cycles_per_frame_at_peak": winstr / (sm_count * 4),
+                 "source": facts.get("source"),
+                 "note": "THE BINDING ROOFLINE: executed warp instructions of project_kernel + raycast_kernel for one frame of this orbit (ncu, "
+                         "static for a given scene and camera) over the live event-timed launch duration, against one instruction per "
+                         "scheduler and cycle (4 schedulers x SMs x max clock)"}
+    out = {
+        "metric": METRIC_RAY, "value": r["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": CONFIG_RAY,
+        "run": {"frames_per_rank_per_step": r["frames"], "partition": "frames k = rank (mod N); " + r["gather"],
+                "l2": f"each rank cycles {SUB} distinct 33 MB frame targets (265 MB > L2); mesh + BVH (~21 MB) stay L2-resident by design, "
+                      "as they are reused every frame",
+                "streams": f"frames alternate over {args.raycast_streams} CUDA streams", "bvh_build_excluded": True,
+                "timed_region_ms_per_rank": r["ms_ranks"], "view_refit_passes": args.view_refit,
+                **({"gather_verified": "every rank's locally rendered frames of the last sub-batch == its slots of rank 0's frame store, bit for bit",
+                    "gather_bytes_per_step_per_rank": r["push_bytes_step"], "full_frame_bytes_per_step_per_rank": 4 * W * H * r["frames"]}
+                   if r["gather_verified"] else {})},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": facts.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "kernel": "raycast_kernel<8> (+ project_kernel, same launch pair)", "kernel_ms": kernel_ms,
+                     "kernel_ms_alone": r["kernel_ms_alone"],
+                     "kernel_ms_note": "kernel_ms = timed region / launch pairs in it (frames overlap on the streams named in run); "
+                                       "kernel_ms_alone = one frame's launch pair with nothing else on the GPU",
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "algorithmic_bytes_note": "4 B/ray BGRA8 written + T x 96 B leaves + (2T-1) x 32 B nodes read once (SURVEY.md 8d; the id and "
+                                               "t planes of its 12 B/ray are not written by the timed call and are not counted)",
+                     "note": "HBM does not bind this kernel (BVH and its per-frame screen-space copy are L2-resident): see `issue` for the unit "
+                             "that does, `fp32` for the arithmetic it amounts to",
+                     "issue": issue,
+                     "fp32": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
+                              "inner_node_visits_per_ray": nodes / (W * H), "triangle_tests_per_ray": tests / (W * H),
+                              "rays_traced_fraction": rays / (W * H),
+                              "flop_model": "per voting lane: 10 float compares per inner node (two screen rectangles + depth bound each) + 45 flop "
+                                            "per Moller-Trumbore test; peak counts FMA as 2 flop, this kernel is compiled -fmad=false for bit-exact parity"}},
+        "frame_filling": r["frame_filling"],
+        "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"],
+    }
+    return out
+
+
+def assemble_ras(args, world, r):
+    hbm_peak, peak_src = peaks()
+    facts = ncu_fact("raster_frame")
+    alg_bytes = 3 * N_TRIS * 32 + RAS_W * RAS_H * 20                               # SURVEY.md section 8(d), per frame
+    achieved = alg_bytes / (r["frame_ms"] * 1e-3) / 1e9
+    return {
+        "metric": METRIC_RAS, "value": r["value"], "unit": "Mtris/s", "ms_per_step": r["ms"] / args.steps, "scaling": "weak", "config": CONFIG_RAS,
+        "run": {"frames_per_rank_per_step": r["frames"], "partition": "frames k = rank (mod N); " + r["gather"],
+                "l2": f"{SUB} independent raster targets per rank (~300 MB of key/colour/record buffers > L2)",
+                "streams": f"one CUDA stream per frame target ({r['streams']})", "timed_region_ms_per_rank": r["ms_ranks"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": facts.get("dram_bytes_per_launch"),
+                     "peak_source": peak_src, "unit_of_work": "one frame = 4 kernels (depth clear, raster_kernel, "
+                     "coverage_kernel, resolve_kernel; the colour clear is folded into the resolve); algorithmic bytes are defined per frame",
+                     "frame_ms": r["frame_ms"], "frame_ms_alone": r["frame_ms_alone"], "algorithmic_bytes_per_frame": alg_bytes},
+        "e2e": r["e2e"], "gpu_launches": r["launches"],
+    }
 
 
 def main():
@@ -659,23 +964,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="raycast", choices=["raycast", "raster"], help="which half of the metric is the primary line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--raycast-streams", type=int, default=4, help="raycast frames of a step alternate over this many CUDA streams")
+    ap.add_argument("--no-tiles", action="store_true", help="skip the image-space tile partition (configs[3] as written)")
+    ap.add_argument("--no-config4", action="store_true", help="skip configs[4] (10M triangles)")
+    ap.add_argument("--only", default=None, choices=["raycast", "raster", "tiles", "config4"], help="dev: run one section only")
+    ap.add_argument("--raycast-streams", type=int, default=4, help="raycast frames alternate over this many CUDA streams")
     ap.add_argument("--raster-streams", type=int, default=1, help="1: one CUDA stream per raster frame target (default), 0: single stream")
+    ap.add_argument("--commit-every", type=int, default=4, help="N>1: sub-batches of 8 frames per rank between two commits (4-byte all-reduce)")
     ap.add_argument("--dense-gather", dest="sparse", action="store_false",
                     help="--gather copy: push whole frames instead of the rect that can differ from the clear colour")
     ap.add_argument("--dense-readback", dest="sparse_readback", action="store_false",
-                    help="e2e: read whole ray-cast frames back instead of the rect that can differ from the clear colour")
-    ap.add_argument("--view-refit", type=int, default=0, help="EXPERIMENTAL, unmeasured: tightening passes over the screen-space nodes "
-                    "(rt_raycast_set_view_refit); 0 = the measured path")
-    ap.add_argument("--region-amax", type=float, default=0.0, help="EXPERIMENTAL, unmeasured: two-level region traversal with this frontier "
-                    "threshold in tiles (rt_raycast_set_region_traversal); 0 = the measured path")
-    ap.add_argument("--raster-gather", default="peer", choices=["peer", "copy"],
-                    help="N>1, raster frames: peer = the kernels store into rank 0's frame store (default, measured); copy = EXPERIMENTAL, "
-                         "not yet measured: render locally, push Raster.content_rect with the copy engine")
+                    help="e2e: read whole frames back instead of the rect that can differ from the clear colour")
+    ap.add_argument("--view-refit", type=int, default=None, help="tightening passes over the screen-space nodes (rt_raycast_set_view_refit)")
+    ap.add_argument("--raster-gather", default="copy", choices=["peer", "copy", "nccl"],
+                    help="N>1, raster frames: copy = render locally, push Raster.content_rect with the copy engine; peer = the kernels "
+                         "store into rank 0's frame store")
     ap.add_argument("--gather", default="copy", choices=["peer", "copy", "nccl"],
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
-                         "IPC-mapped frame store while the next frame traces (default: fastest from N=4 up); peer = the kernels store "
-                         "straight into that frame store over NVLink (fused); nccl = send/recv gather.  Raster frames: peer unless nccl")
+                         "IPC-mapped frame store while the next frames trace; peer = the kernels store straight into that frame store "
+                         "over NVLink (fused); nccl = send/recv gather")
+    ap.add_argument("--tiles-gather", default="peer", choices=["peer", "copy"], help="N>1, tile partition: how stripes reach rank 0's frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -690,20 +997,29 @@ def main():
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    rank, world, local = dist_setup(args.gpus)
-    if args.view_refit or args.region_amax:
-        from rendertoy_b200 import _native
-        _native.call("rt_raycast_set_view_refit", args.view_refit)
-        _native.call("rt_raycast_set_region_traversal", args.region_amax)
-    ray, rows = bench_raycast(args, rank, world)
-    if args.view_refit or args.region_amax:
-        ray["config"]["experimental"] = {"view_refit_passes": args.view_refit, "region_amax_tiles": args.region_amax}
-    ras = bench_raster(args, rank, world, rows)
+    rank, world, local = dist_setup()
+    from rendertoy_b200 import _native, scenes
+    import rendering as ren
+    if args.view_refit is None:
+        args.view_refit = DEFAULT_VIEW_REFIT
+    _native.call("rt_raycast_set_view_refit", args.view_refit)
+    rows = scenes.dragon(N_TRIS)
+    vb = upload(ren, rows)
+    want = (lambda name: args.only in (None, name))
+    ray = ras = tiles = cfg4 = None
+    if want("raycast"):
+        ray = assemble_ray(args, world, bench_raycast(args, rank, world, rows, vb))
+    if want("raster"):
+        ras = assemble_ras(args, world, bench_raster(args, rank, world, rows, vb))
+    if want("tiles") and not args.no_tiles:
+        tiles = bench_tiles(args, rank, world, rows, vb)
+    if want("config4") and not args.no_config4:
+        cfg4 = bench_config4(args, rank, world, rows)
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.only is None:
             import oracle
             oracle.build()
-            cores = oracle.num_threads()
+            cores = cpu_threads()
             cpu_raycast(rows, 1)
             v, dt, nf = cpu_raycast(rows, 2, min_seconds=10.0)
             ray["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
@@ -714,17 +1030,27 @@ def main():
             ras["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": cores, "kind": "port",
                                    "sample": f"{nf} frames of 1920x1080 x 100000 triangles in {dt:.1f} s; restated reference pipeline "
                                              "(oracle/raster_oracle.c, OpenMP)"}
-        primary, secondary = (ray, ras) if args.path == "raycast" else (ras, ray)
-        if args.path == "raster":
-            for k in ("n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "clocks"):
-                primary.setdefault(k, ray.get(k))
-        primary["secondary"] = secondary
+        if args.only is not None:
+            primary = {"only": args.only, "n_gpus": world, "raycast": ray, "raster": ras, "tiles": tiles, "config4": cfg4}
+        else:
+            primary, secondary = (ray, ras) if args.path == "raycast" else (ras, ray)
+            if args.path == "raster":
+                for k in ("n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "clocks"):
+                    primary.setdefault(k, ray.get(k))
+            primary["secondary"] = secondary
+            if tiles is not None:
+                primary["tiles"] = tiles
+            if cfg4 is not None:
+                primary["config4"] = cfg4
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(primary) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+
+
+DEFAULT_VIEW_REFIT = 2   # measured on B200 (profiles/r02c_refit*.json): 0 -> 70.9, 1 -> 73.4, 2 -> 74.2, 4 -> 72.1 Grays/s on the cfg4 orbit
 
 
 if __name__ == "__main__":

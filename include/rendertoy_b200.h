@@ -220,6 +220,12 @@ int rt_peer_close(void *d_ptr);
  * pointer may be local device, peer-mapped device or pinned host memory. */
 int rt_copy_rect(void *d_dst, int64_t dst_pitch_bytes, const void *d_src, int64_t src_pitch_bytes, int64_t width_bytes,
                       int64_t rows, void *stream);
+/* The gather of the image-space partition: move the row stripes a rank owns -- rows y in [y0, y1] with
+ * (y / stripe_rows) % mod == rem, bytes [x_bytes, x_bytes + width_bytes) of each row -- from the frame at d_src to the same
+ * place in the frame at d_dst (same row pitch; local, peer-mapped or pinned host memory).  One 3-D copy-engine transfer for
+ * the whole stripes plus at most two 2-D ones for stripes that [y0, y1] cuts. */
+int rt_copy_stripes(void *d_dst, const void *d_src, int64_t pitch_bytes, int64_t x_bytes, int64_t width_bytes, int64_t y0, int64_t y1,
+                    int stripe_rows, int mod, int rem, void *stream);
 
 #ifdef __cplusplus
 }

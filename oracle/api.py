@@ -47,6 +47,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_threads(n):
+    """OpenMP threads for every following oracle call (bench.py: os.cpu_count(), whatever OMP_NUM_THREADS says)."""
+    lib().orc_set_threads(int(n))
+    return num_threads()
+
+
 def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 

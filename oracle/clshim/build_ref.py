@@ -7,9 +7,9 @@ for the host CPU.  Outputs: oracle/_ref/clprog_*.{cpp,so} (git-ignored).  Refere
 lie; nothing is copied into the repo.  tests/golden/*.npz are produced by make_golden.py from these programs.
 
 It also byte-compiles the tutorial scripts that drive the two hot paths (tutorials/lesson06, 08, 09) where they lie into
-oracle/_ref/tutorials/*.pyc -- the Python counterpart of compiling a C reference into oracle/_ref/*.so: the GPU box has
+oracle/_ref/tutorials/*.pycode (a .pyc under another extension: the gpurun snapshot drops *.pyc) -- the Python counterpart of compiling a C reference into oracle/_ref/*.so: the GPU box has
 no /root/reference, and tests/test_tutorials_gpu.py executes the UNMODIFIED tutorial programs against this package
-(runpy on the .py here, on the .pyc there).  The .pyc files are git-ignored build outputs like the .so files.
+(runpy on the .py here, exec of the unmarshalled code object there).  They are git-ignored build outputs like the .so files.
 """
 import glob
 import os
@@ -50,7 +50,7 @@ def compile_tutorials():
     for name in TUTORIALS:
         src = os.path.join(REFERENCE, "tutorials", name + ".py")
         if os.path.exists(src):
-            py_compile.compile(src, cfile=os.path.join(out, name + ".pyc"), dfile=f"<reference>/tutorials/{name}.py", doraise=True,
+            py_compile.compile(src, cfile=os.path.join(out, name + ".pycode"), dfile=f"<reference>/tutorials/{name}.py", doraise=True,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     print("tutorials: byte-compiled", ", ".join(TUTORIALS), "-> oracle/_ref/tutorials/")
 

@@ -491,6 +491,16 @@ void orc_clear_color(uint8_t *bgra, int64_t n, const float rgba[4])
     for (int64_t i = 0; i < n; ++i) memcpy(bgra + 4 * i, px, 4);
 }
 
+/* bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline is "all host cores", set explicitly */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -67,4 +67,55 @@ int rt_copy_rect(void *d_dst, int64_t dst_pitch_bytes, const void *d_src, int64_
     return RT_OK;
 }
 
+// The image-space partition's gather: a rank that rendered its row stripes of a frame locally moves exactly
+// those -- rows y in [y0, y1] with (y / stripe_rows) % mod == rem, columns [x_bytes, x_bytes + width_bytes) -- into the same
+// place of the frame at d_dst (same pitch on both sides).  Whole stripes between the first and the last go as ONE 3-D
+// copy-engine transfer (a stripe = a 2-D slice, slices mod * stripe_rows rows apart), the two that [y0, y1] may cut as 2-D ones.
+int rt_copy_stripes(void *d_dst, const void *d_src, int64_t pitch_bytes, int64_t x_bytes, int64_t width_bytes, int64_t y0, int64_t y1,
+                    int stripe_rows, int mod, int rem, void *stream)
+{
+    RT_REQUIRE(d_dst && d_src && pitch_bytes > 0 && x_bytes >= 0 && width_bytes >= 0 && x_bytes + width_bytes <= pitch_bytes, "frame geometry");
+    RT_REQUIRE(stripe_rows >= 1 && mod >= 1 && rem >= 0 && rem < mod && y0 >= 0, "stripes");
+    if (width_bytes == 0 || y1 < y0) return RT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *dst = (char *)d_dst + x_bytes;
+    const char *src = (const char *)d_src + x_bytes;
+    auto copy2d = [&](int64_t ya, int64_t yb) -> cudaError_t { // rows [ya, yb]
+        return cudaMemcpy2DAsync(dst + ya * pitch_bytes, (size_t)pitch_bytes, src + ya * pitch_bytes, (size_t)pitch_bytes, (size_t)width_bytes,
+                                 (size_t)(yb - ya + 1), cudaMemcpyDefault, st);
+    };
+    // owned stripes s = rem + j * mod that meet [y0, y1]
+    const int64_t s_lo = y0 / stripe_rows, s_hi = y1 / stripe_rows;
+    int64_t j0 = s_lo <= rem ? 0 : (s_lo - rem + mod - 1) / mod;
+    if (rem + j0 * mod > s_hi) return RT_OK;
+    const int64_t j1 = (s_hi - rem) / mod;
+    int64_t ja = j0, jb = j1; // [ja, jb]: stripes wholly inside [y0, y1]
+    const int64_t first = rem + j0 * (int64_t)mod, last = rem + j1 * (int64_t)mod;
+    if (first * stripe_rows < y0 || (first + 1) * stripe_rows - 1 > y1) {
+        const int64_t ya = first * stripe_rows > y0 ? first * stripe_rows : y0, yb = (first + 1) * stripe_rows - 1 < y1 ? (first + 1) * stripe_rows - 1 : y1;
+        RT_CUDA(copy2d(ya, yb));
+        ja = j0 + 1;
+    }
+    if (j1 >= ja && (last + 1) * stripe_rows - 1 > y1) {
+        RT_CUDA(copy2d(last * stripe_rows, y1));
+        jb = j1 - 1;
+    }
+    if (jb < ja) return RT_OK;
+    const int64_t ya = (rem + ja * (int64_t)mod) * stripe_rows;
+    if (jb == ja) { RT_CUDA(copy2d(ya, ya + stripe_rows - 1)); return RT_OK; }
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<char *>(src) + ya * pitch_bytes, (size_t)pitch_bytes, (size_t)width_bytes, (size_t)mod * stripe_rows);
+    p.dstPtr = make_cudaPitchedPtr(dst + ya * pitch_bytes, (size_t)pitch_bytes, (size_t)width_bytes, (size_t)mod * stripe_rows);
+    p.extent = make_cudaExtent((size_t)width_bytes, (size_t)stripe_rows, (size_t)(jb - ja + 1));
+    p.kind = cudaMemcpyDefault;
+    if (cudaMemcpy3DAsync(&p, st) != cudaSuccess) { // e.g. a driver that refuses 3-D copies into IPC-mapped memory: stripe by stripe
+        (void)cudaGetLastError();
+        for (int64_t j = ja; j <= jb; ++j) {
+            const int64_t y = (rem + j * (int64_t)mod) * stripe_rows;
+            RT_CUDA(copy2d(y, y + stripe_rows - 1));
+        }
+    }
+    return RT_OK;
+}
+
 } // extern "C"

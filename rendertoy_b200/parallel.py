@@ -210,6 +210,28 @@ class FrameStore:
             self._copier = SparseFrameCopier(self.width, self.height)
         return self._copier.copy(k, self._base + k * self.frame_bytes, src_ptr, content, stream)
 
+    def push_stripes(self, k, src_ptr, content, stripes, stream):
+        """Image-space partition: copy-engine push of the row stripes (rows, mod, rem) this rank rendered of frame k, from its
+        local full-size frame at src_ptr into slot k -- again only the pixel rect that can differ from what the slot holds
+        (cover_rect of the slot's previous content and this frame's; every rank keeps that history for its own stripes).
+        Returns the bytes enqueued (an upper bound: whole stripes of the rect)."""
+        if self._copier is None:
+            self._copier = SparseFrameCopier(self.width, self.height)
+        c = self._copier
+        key = ("stripes", k)
+        r = cover_rect(c._content.get(key), content, self.width, self.height)
+        c._content[key] = content
+        if r is None:
+            return 0
+        x0, y0, x1, y1 = r
+        rows, mod, rem = stripes
+        self._native.call("rt_copy_stripes", self._base + k * self.frame_bytes, src_ptr, 4 * self.width, 4 * x0, 4 * (x1 - x0 + 1), y0, y1,
+                          rows, mod, rem, stream)
+        n = 4 * (x1 - x0 + 1) * sum(min(y1, (s + 1) * rows - 1) - max(y0, s * rows) + 1
+                                    for s in range(y0 // rows, y1 // rows + 1) if s % mod == rem)
+        c.bytes_moved += n
+        return n
+
     def frames(self):
         """(n_frames, H, W) int32 view -- meaningful on rank `dst` after commit()."""
         return self.memory.view(torch.int32).view(self.n_frames, self.height, self.width)

@@ -112,6 +112,36 @@ def instanced(base_rows, grid=10, scale=0.1, seed=1):
     return out
 
 
+def instanced_device(ren, base_rows, grid=10, scale=0.1, seed=1):
+    """instanced() built on the GPU, straight into a MeshVertex device buffer (torch as plumbing: no 2.4 GB host array, no
+    2.4 GB upload for dragon10M).  Same instances, same rng draws; coordinates may differ from the numpy version in the last
+    bit (the 3x3 rotation is written out instead of going through BLAS) -- bench.py uses this, the parity tests use instanced()."""
+    import torch
+    rng = np.random.default_rng(seed)
+    n = base_rows.shape[0]
+    vb = ren.create_buffer(n * grid * grid, ren.MeshVertex)
+    out = vb.tensor().view(torch.float32).view(-1, 20)
+    base = torch.from_numpy(np.ascontiguousarray(base_rows)).to(out.device)
+    k = 0
+    for gx in range(grid):
+        for gz in range(grid):
+            yaw = rng.uniform(0, 2 * np.pi)
+            c, s = float(np.float32(np.cos(yaw))), float(np.float32(np.sin(yaw)))
+            blk = out[k * n:(k + 1) * n]
+            for o in (0, 4):            # positions, normals: row vector times [[c, 0, -s], [0, 1, 0], [s, 0, c]]
+                x, y, z = base[:, o], base[:, o + 1], base[:, o + 2]
+                f = float(np.float32(scale)) if o == 0 else 1.0
+                blk[:, o] = (x * c + z * s) * f
+                blk[:, o + 1] = y * f
+                blk[:, o + 2] = (z * c - x * s) * f
+            blk[:, 0] += float(np.float32((gx + 0.5) / grid - 0.5))
+            blk[:, 2] += float(np.float32((gz + 0.5) / grid - 0.5))
+            blk[:, 8:10] = base[:, 8:10]
+            k += 1
+    vb.device_written()
+    return vb
+
+
 def write_obj(path, rows, with_uv=False):
     """Write a soup as a Wavefront OBJ (one v/vn[/vt] per corner, f in file order)."""
     with open(path, "w") as fh:

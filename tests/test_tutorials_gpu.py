@@ -9,8 +9,9 @@ and time.perf_counter is a deterministic clock.  The last frame (render target, 
 the oracle's restatement of the reference pipeline for the matrices the script left in its globals buffer.
 
 Where the program text comes from: /root/reference/tutorials/*.py when that checkout exists (the build container), else
-oracle/_ref/tutorials/*.pyc -- byte-compiled from those files, in place, by oracle/clshim/build_ref.py (a git-ignored build
-output that travels to the GPU box like oracle/_ref/*.so; the GPU box has no /root/reference).  Nothing here is a retyped copy.
+oracle/_ref/tutorials/*.pycode -- byte-compiled from those files, in place, by oracle/clshim/build_ref.py (a .pyc under another
+name, because the gpurun snapshot drops *.pyc; a git-ignored build output that travels to the GPU box like oracle/_ref/*.so;
+the GPU box has no /root/reference).  Nothing here is a retyped copy.
 """
 import os
 import runpy
@@ -32,10 +33,10 @@ def _program(name):
     src = os.path.join(REFERENCE, "tutorials", name + ".py")
     if os.path.exists(src):
         return src
-    pyc = os.path.join(ROOT, "oracle", "_ref", "tutorials", name + ".pyc")
+    pyc = os.path.join(ROOT, "oracle", "_ref", "tutorials", name + ".pycode")
     if os.path.exists(pyc):
         return pyc
-    pytest.skip(f"{name}: neither the reference checkout nor oracle/_ref/tutorials/{name}.pyc is here "
+    pytest.skip(f"{name}: neither the reference checkout nor oracle/_ref/tutorials/{name}.pycode is here "
                 "(run __graft_entry__.build() where /root/reference exists)")
 
 
@@ -59,7 +60,14 @@ def _run_tutorial(name, tmp_path, monkeypatch, frames=3, n_tris=3000, texture=Fa
         clock[0] += 0.173
         return clock[0]
     monkeypatch.setattr(time, "perf_counter", fake_clock)
-    ns = runpy.run_path(path, run_name="__main__")
+    if path.endswith(".py"):
+        ns = runpy.run_path(path, run_name="__main__")
+    else:       # what `python file.pyc` does: 16-byte header, then the marshalled module code object
+        import marshal
+        with open(path, "rb") as fh:
+            code = marshal.loads(fh.read()[16:])
+        ns = {"__name__": "__main__", "__file__": code.co_filename, "__builtins__": __builtins__}
+        exec(code, ns)
     dumps = sorted(os.listdir(tmp_path / "dump"))
     assert len(dumps) == frames, f"the tutorial loop presented {len(dumps)} frames, expected {frames}"
     from PIL import Image

@@ -164,7 +164,19 @@ __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, 
 // Candidate cells (those the division-free sign test cannot reject) are compacted through a per-warp
 // shared-memory ring, so the exact test + depth atomics always run with full warps.
 
-constexpr int RW = 4;           // warps per raster block
+#ifndef RT_RASTER_RW
+#define RT_RASTER_RW 4
+#endif
+#ifndef RT_RASTER_MINB
+// resident blocks per SM the compiler must allow for (register cap); -D overrides for A/B builds.  Measured on B200 (cfg2, 8 frame
+// streams): uncapped (78 registers) 51.1 us per frame, 7 blocks (72 registers, no spills for lesson08) 49.6, 8 blocks 49.5,
+// 2- or 8-warp blocks 49.4 / 49.7; resolve_kernel at 2 or 4 blocks per SM instead of 3: 53.2 / 53.5.
+#define RT_RASTER_MINB (SHADER == RT_SHADER_LESSON08 && !SC ? 7 : 1)
+#endif
+#ifndef RT_RESOLVE_MINB
+#define RT_RESOLVE_MINB 3
+#endif
+constexpr int RW = RT_RASTER_RW; // warps per raster block
 constexpr int SMALL_MAX = 256;  // largest bbox (cells) rasterized inline by the owning warp
 constexpr int QUADS = 32;       // a queued work item = 32 row-quads (4 cells along x each) of a large primitive
 constexpr int RING = 160;       // per-warp candidate stack: < 32 left over + up to 4 new per lane per pass
@@ -418,7 +430,7 @@ __device__ __forceinline__ void cover_rows(const Slot *my_slots, unsigned *my_ri
 }
 
 template <int SHADER, bool SC>
-__global__ void __launch_bounds__(RW * 32, SC ? 5 : (SHADER == RT_SHADER_LESSON08 ? 7 : 6)) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
+__global__ void __launch_bounds__(RW * 32, RT_RASTER_MINB) raster_kernel(const DrawArgs a, WorkCtl *ctl, uint2 *items, Slot *bigslots, const unsigned capacity)
 {
     __shared__ Slot slots[RW][32];
     __shared__ unsigned ring[RW][RING];
@@ -453,27 +465,22 @@ __global__ void __launch_bounds__(RW * 32, SC ? 5 : (SHADER == RT_SHADER_LESSON0
                 if (lane >= d) incl += v;
             }
             const int tot = __shfl_sync(FULL, incl, 31);
-            // claim [base, base + tot) only if it fits: n_items never exceeds the capacity and never shrinks, so every slot
-            // below it is owned by exactly one warp, which fills it before the kernel ends (no give-back, no holes)
-            unsigned base = 0xffffffffu;
-            if (lane == 0) {
-                unsigned seen = *(volatile unsigned *)&ctl->n_items;
-                while ((unsigned long long)seen + (unsigned)tot <= capacity) {
-                    const unsigned prev = atomicCAS(&ctl->n_items, seen, seen + (unsigned)tot);
-                    if (prev == seen) { base = seen; break; }
-                    seen = prev;
-                }
-            }
+            // n_items only grows (no give-back): every slot below min(n_items, capacity) is owned by exactly one warp.  A warp whose
+            // range does not fit rasterizes its large primitives inline and fills what it reserved below the capacity with null
+            // items (coverage_kernel skips them), so the consumer never reads an unwritten slot.
+            unsigned base = capacity;
+            if (lane == 0 && *(volatile unsigned *)&ctl->n_items < capacity) base = atomicAdd(&ctl->n_items, (unsigned)tot);
             base = __shfl_sync(FULL, base, 0);
-            if (base != 0xffffffffu) {
+            if (base + (unsigned)tot <= capacity) {
                 unsigned w = base + (unsigned)(incl - nchunks);
                 if (nchunks) {
                     bigslots[w] = mine; // setup travels with the first item: coverage_kernel recomputes nothing
                     for (int j = 0; j < nchunks; ++j) items[w + j] = make_uint2(w, (unsigned)j);
                     ncells = 0; // handed over
                 }
-            } else if (lane == 0) {
-                atomicAdd(&ctl->overflowed, 1u); // queue full: these primitives are rasterized inline below
+            } else {
+                for (unsigned w = base + (unsigned)lane; w < capacity; w += 32u) items[w] = make_uint2(0xffffffffu, 0u);
+                if (lane == 0) atomicAdd(&ctl->overflowed, 1u);
             }
         }
 
@@ -511,15 +518,16 @@ __global__ void __launch_bounds__(RW * 32, SC ? 5 : (SHADER == RT_SHADER_LESSON0
 // sign-test their 4 cells; the survivors of the whole warp are then dealt out one per lane (ballot + find-nth-set)
 // so the exact test -- 3 IEEE divisions, depth, 64-bit atomicMin -- always runs on full warps.
 template <int SHADER, bool SC>
-__global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items, const Slot *bigslots)
+__global__ void __launch_bounds__(128) coverage_kernel(const DrawArgs a, const WorkCtl *ctl, const uint2 *items, const Slot *bigslots, const unsigned capacity)
 {
     const unsigned FULL = 0xffffffffu;
-    const unsigned n_items = ctl->n_items;
+    const unsigned n_raw = ctl->n_items, n_items = n_raw < capacity ? n_raw : capacity; // the producers' counter may run past the queue's capacity
     const int lane = threadIdx.x & 31;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int W = a.width, H = a.height;
     for (unsigned i = warp; i < n_items; i += n_warps) {
         const uint2 it = items[i];
+        if (it.x == 0xffffffffu) continue; // reserved by a warp whose range did not fit
         const float4 *sp = reinterpret_cast<const float4 *>(bigslots + it.x);
         const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3), s4 = __ldcg(sp + 4), s5 = __ldcg(sp + 5);
         Edges e;
@@ -661,7 +669,7 @@ __device__ __forceinline__ void resolve_pixel(const ResolveArgs &a, int x, int y
 // y+8, y+12).  The four key loads are issued before any is used: the kernel is bound by the latency of that one
 // dependent load per pixel, so memory-level parallelism is what buys time here.
 template <int SHADER>
-__global__ void __launch_bounds__(256, 3) resolve_kernel(const ResolveArgs a)
+__global__ void __launch_bounds__(256, RT_RESOLVE_MINB) resolve_kernel(const ResolveArgs a)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->n_items = 0; // queue drained: re-arm for the next draw
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -821,8 +829,8 @@ int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scr
         else raster_kernel<SHADER, false><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
         RT_CUDA(cudaGetLastError());
         if (cap > 0) {
-            if (da.scissor) coverage_kernel<SHADER, true><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
-            else coverage_kernel<SHADER, false><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots);
+            if (da.scissor) coverage_kernel<SHADER, true><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
+            else coverage_kernel<SHADER, false><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
             RT_CUDA(cudaGetLastError());
         }
     }

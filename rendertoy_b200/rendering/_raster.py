@@ -50,6 +50,18 @@ _BUILTIN_SHADERS = {
 }
 
 
+def transforms48(world, view, proj):
+    """(World, View, Proj) -> 48 float32, row-major: each matrix may be a float4x4 value, the 16-tuple make_float4x4 /
+    matmul return for array arguments (rendering/_core.py:127-181), or any 4x4 / 16-element array."""
+    out = np.empty(48, np.float32)
+    for i, m in enumerate((world, view, proj)):
+        a = np.asarray(m)
+        a = a.reshape(-1).view(np.float32) if a.dtype == _core.float4x4 else np.asarray(a, dtype=np.float32).reshape(-1)
+        assert a.size == 16, "expected a 4x4 matrix"
+        out[16 * i:16 * i + 16] = a
+    return out
+
+
 def _struct_fields(dtype):
     return [(n, dtype.fields[n][0], dtype.fields[n][1]) for n in dtype.names]
 
@@ -74,6 +86,7 @@ class Raster:
         self._depth_buffer = DepthView(self._key_buffer, n_pixels)
         self._fill_mode = FillMode.WIREFRAME
         self._keys_armed = False
+        self._gl_once = None    # draw_frame(): the (c_float * 48) the caller prepared, handed to the next draw as is
         self._owner = None      # set_scissor(): (c_int * 7) {x0, y0, x1, y1, stripe rows, mod, rem} handed to the native draws
         self._draws = None      # draws since the last clear(render_target): [(vertex buffer, its version, globals)], None = unknown
 
@@ -288,6 +301,40 @@ class Raster:
         desc = g[g.dtype.names[0]]
         return _core.__MEMORY_POOL__.texture_handle(int(desc["offset"]))
 
+    def draw_frame(self, vertex_buffer, index_buffer=None, transforms=None, clear_color=0.0, clear_depth=1.0):
+        """One tutorial frame in ONE call (not in the reference API): what lesson08:90-105 spells as
+
+            with mapped(shader_globals) as map: map["World"], map["View"], map["Proj"] = ...
+            clear(raster.get_render_target()); clear(raster.get_depth_buffer(), 1.0); raster.draw_triangles(vb, ib)
+
+        transforms: None (keep what the globals buffer holds), a (World, View, Proj) tuple of float4x4 values, or 48 floats /
+        a (c_float * 48) prepared once per camera.  The globals buffer is updated, so the four calls above and this one are
+        interchangeable frame by frame; the result is bit-identical.  It exists because the four calls cost 35-40 us of
+        Python per frame while the B200 needs ~50 us for the frame itself.  clear_color: a float or
+        None (no clear); clear_depth: a float or None."""
+        import ctypes
+        assert self._generic is None, "draw_frame needs the built-in (tutorial) shader pairs"
+        if transforms is not None:
+            if isinstance(transforms, tuple):
+                transforms = transforms48(*transforms)
+            g = self.vertex_shader_globals
+            st = g._st
+            if st.host is not None:      # straight into the struct's host shadow (what mapped() would do), no device traffic
+                if isinstance(transforms, ctypes.Array):
+                    ctypes.memmove(st.host.ctypes.data + g.offset, transforms, 192)
+                    self._gl_once = transforms
+                else:
+                    st.host[g.offset:g.offset + 192] = np.ascontiguousarray(transforms, np.float32).view(np.uint8)
+                st.host_valid, st.dev_valid = True, False
+                st.version += 1
+            else:
+                g.set(np.ascontiguousarray(transforms, np.float32).view(g.dtype).reshape(()))
+        if clear_color is not None:
+            self._render_target._pending_clear = _native.float4_const(float(clear_color))
+        if clear_depth is not None:
+            self._depth_buffer._pending = int(np.float32(clear_depth).view(np.uint32))
+        self.draw_triangles(vertex_buffer, index_buffer)
+
     def draw_triangles(self, vertex_buffer, index_buffer):
         """Raster.draw_triangles (:416-437).  index_buffer None -> triangle soup; else int32 indices.
         Accumulates into the persistent depth / colour targets exactly like consecutive reference draws."""
@@ -310,7 +357,8 @@ class Raster:
             need = _native.lib().rt_raster_scratch_bytes(self.shader_id, primitive_count, rt.width, rt.height)
             self._scratch = create_buffer(int(need), np.uint8)   # zero-filled: the control block starts armed
             self._scratch_tris = primitive_count
-        gl, clear = self._vs_globals(), rt.take_pending_clear()
+        gl, clear = self._gl_once or self._vs_globals(), rt.take_pending_clear()
+        self._gl_once = None
         self._note_draw(vertex_buffer, gl, clear is not None)
         _native.call("rt_raster_draw_triangles", pos4.data_ptr(), nrm4.data_ptr(), idx_ptr, primitive_count, self.shader_id,
                      gl, self._texture_handle(), rt.width, rt.height, self._key_buffer.ptr,

@@ -260,3 +260,27 @@ def test_scissor_rect_and_points(ren, oracle):
         draw(vb, None)
         assert np.array_equal(raster.get_depth_buffer().get().reshape(h, w), ref.depth)
         assert np.array_equal(raster.get_render_target().get(), ref.bgra)
+
+
+def test_draw_frame_equals_the_four_tutorial_calls(ren, oracle):
+    """Raster.draw_frame(vb, ib, transforms) == mapped(globals) + clear + clear + draw_triangles, bit for bit, and leaves the
+    globals buffer holding the same matrices; with transforms=None it draws with what the buffer holds."""
+    import ctypes
+    w, h = 640, 360
+    rows = scenes.dragon(8_000)
+    vb = _upload(ren, rows)
+    cam = scenes.lesson_camera(ren, 8, 1.1, w, h)
+    a, ga = lessons.build_lesson08(ren, ren.create_presenter(w, h).get_render_target())
+    lessons.set_transforms(ren, ga, *cam)
+    lessons.render_frame(ren, a, vb)
+    ref = oracle.draw_triangles(8, w, h, rows, lessons.globals_as_floats(ga))
+    g48 = lessons.globals_as_floats(ga)
+    for transforms in (cam, g48, (ctypes.c_float * 48)(*g48.tolist())):
+        b, gb = lessons.build_lesson08(ren, ren.create_presenter(w, h).get_render_target())
+        b.get_depth_buffer().set(np.full(w * h, 0x12345678, np.uint32))       # stale contents the frame's clears must remove
+        b.draw_frame(vb, None, transforms)
+        assert np.array_equal(lessons.globals_as_floats(gb), g48)
+        assert np.array_equal(b.get_depth_buffer().get().reshape(h, w), ref.depth)
+        assert np.array_equal(b.get_render_target().get(), ref.bgra)
+        b.draw_frame(vb, None)                                                  # same matrices, from the buffer
+        assert np.array_equal(b.get_render_target().get(), ref.bgra)

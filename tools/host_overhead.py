@@ -17,6 +17,15 @@ def frames(n):
         lessons.render_frame(ren, raster, vb)
 frames(20); torch.cuda.synchronize()
 t0 = time.perf_counter(); frames(300); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-print(f"enqueue {1e6*(t1-t0)/300:.1f} us/frame, total {1e6*(t2-t0)/300:.1f} us/frame")
+print(f"tutorial calls: enqueue {1e6*(t1-t0)/300:.1f} us/frame, total {1e6*(t2-t0)/300:.1f} us/frame")
+import ctypes
+from rendering._raster import transforms48
+g48 = [(ctypes.c_float * 48)(*transforms48(*c).tolist()) for c in cams]
+def frames2(n):
+    for k in range(n):
+        raster.draw_frame(vb, None, g48[k])
+frames2(20); torch.cuda.synchronize()
+t0 = time.perf_counter(); frames2(300); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"draw_frame: enqueue {1e6*(t1-t0)/300:.1f} us/frame, total {1e6*(t2-t0)/300:.1f} us/frame")
 pr = cProfile.Profile(); pr.enable(); frames(300); pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

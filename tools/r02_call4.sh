@@ -25,4 +25,4 @@ if x: t=x["tiles"]; print("tiles(copy) ray", round(t["raycast"]["value"]), t["ra
 x=load(f"gpurun_out/r02d_ray_c1_n{N}.json")
 if x: print("ray commit-every 1", round(x["raycast"]["value"]), x["raycast"]["run"]["timed_region_ms_per_rank"])
 PY
-tail -5 gpurun_out/r02d_*_n$N.err | tail -30
+for f in gpurun_out/r02d_*_n$N.err; do tail -n 3 $f; done

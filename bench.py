@@ -32,11 +32,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_TRIS = 100_000
+N_TRIS = int(os.environ.get("RENDERTOY_B200_TRIS", "100000"))   # (the override is a dev knob: host-bound or GPU-bound?)
 RAY_W, RAY_H = 3840, 2160
 RAS_W, RAS_H = 1920, 1080
 ORBIT = 256       # World = rotate(2*pi*k/256, y)  
-SUB = 8           # frames per sub-batch = distinct frame targets a rank cycles through (8 x 33 MB > L2)
+SUB = int(os.environ.get("RENDERTOY_B200_SUB", "8"))   # frames per sub-batch = distinct frame targets a rank cycles through (8 x 33 MB > L2)
 RAY_FRAMES = int(os.environ.get("RENDERTOY_B200_RAY_FRAMES", "512"))     # frames per rank and step
 RAS_FRAMES = int(os.environ.get("RENDERTOY_B200_RAS_FRAMES", "1024"))
 TILE_FRAMES = int(os.environ.get("RENDERTOY_B200_TILE_FRAMES", "256"))   # frames per step (all ranks together) in the tile partition
@@ -402,7 +402,7 @@ def bench_raycast(args, rank, world, rows, vb, W=RAY_W, H=RAY_H, lesson=6, frame
     kernel_ms = ms_local / (args.steps * F)      # timed region / launch pairs in it (frames overlap on the streams)
     out = {"value": value, "ms": ms, "ms_ranks": ms_ranks, "kernel_ms": kernel_ms, "clocks": clocks, "frames": F,
            "gather": gather_text(loop, args.sparse), "gather_verified": gather_ok, "push_bytes_step": push_bytes_step,
-           "launches": (2 + args.view_refit) * F * args.steps, "view_nodes": rc.n_triangles <= 1 << 18}
+           "launches": (2 + (1 if args.view_refit else 0)) * F * args.steps, "view_nodes": rc.n_triangles <= 1 << 18}
     if not full:
         loop.close()
         return out
@@ -1053,7 +1053,7 @@ def main():
         dist.destroy_process_group()
 
 
-DEFAULT_VIEW_REFIT = 2   # measured on B200 (profiles/r02c_refit*.json): 0 -> 70.9, 1 -> 73.4, 2 -> 74.2, 4 -> 72.1 Grays/s on the cfg4 orbit
+DEFAULT_VIEW_REFIT = 4   # iterations inside the one view_refit_kernel launch; measured on B200 (profiles/r02f_refit_iterations.txt): 0 -> 70.9, 2 -> 75.1, 4 -> 76.2, 8 -> 74.4, 16 -> 71.8 Grays/s on the cfg4 orbit
 
 
 if __name__ == "__main__":

@@ -77,6 +77,17 @@ static inline int rt_owner_parse(const int32_t *owner7, int width, int height, R
     return 1;
 }
 
+// prefetch.global.L1 (LEVEL 1) / .L2 (LEVEL 2) of the line holding p; nothing when compiled for the host (tools/cuda_emu)
+template <int LEVEL> __device__ __forceinline__ void rt_prefetch(const void *p)
+{
+#ifdef __CUDACC__
+    if (LEVEL == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // normalize((float3)(1,1,1)).x, correctly rounded (lesson08:42)
 #define RT_INV_SQRT3 0.57735026918962576f
 

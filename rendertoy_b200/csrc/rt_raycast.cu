@@ -150,17 +150,19 @@ __global__ void __launch_bounds__(128) project_kernel(const ProjectArgs p)
     p.vnodes[i] = v;
 }
 
-// EXPERIMENTAL, OFF BY DEFAULT, NOT YET RUN ON A GPU (written after the round's GPU budget was spent; see DESIGN.md section 8
-// and tools/refit_experiment.py for the CPU estimate: -25 % node visits per tile packet with 4 passes, -32 % converged).
-// project_kernel gives an inner child the rectangle of its projected 3-D box.  The union of that child's own two
-// rectangles -- which end, at the leaves, in triangle-tight rectangles -- is never larger and for slanted geometry much
-// smaller, likewise the nearer of their depth bounds.  One pass tightens every node from its children's current values, in
-// place.  That is safe without any ordering or atomicity: a rectangle component only ever moves inwards and a depth bound only
-// up, each stays a valid bound at every moment, so whatever mix of old and new values a thread reads gives a valid (if
-// looser) result.  PLOC hands node ids out downwards (children have larger ids than their parents), so the thread -> node
-// mapping is reversed: the blocks scheduled first hold the deepest nodes and one pass usually carries tightness up several
-// levels.  Hits cannot change: every leaf rectangle is untouched and every ancestor keeps containing it.
-__global__ void __launch_bounds__(128) view_refit_kernel(ViewNode *v, long long n_inner)
+// project_kernel gives an inner child the rectangle of its projected 3-D box.  The union of that child's own two rectangles --
+// which end, at the leaves, in triangle-tight rectangles -- is never larger and for slanted geometry much smaller, likewise
+// the nearer of their depth bounds.  view_refit_kernel tightens every node from its children's CURRENT values, in place, `iters`
+// times inside ONE launch (chaotic relaxation).  That is safe without any ordering or atomicity: a rectangle component only
+// ever moves inwards and a depth bound only up, each stays a valid bound at every moment, so whatever mix of old and new
+// values a thread reads (128-bit loads through L2, never L1) gives a valid, if looser, result.  A 100k-triangle tree is a
+// single wave of threads, so an iteration costs one L2 round trip instead of a launch: tightness climbs at least one level
+// per iteration (PLOC hands node ids out downwards, so with the reversed thread -> node mapping the blocks scheduled first
+// hold the deepest nodes and it usually climbs several).  Hits cannot change: every leaf rectangle is untouched and every
+// ancestor keeps containing it (tests: bit-identical hit records for 1..16 iterations, CPU emulator and B200).
+// Measured on B200 (cfg4 frame / lesson08 camera at 4K, one frame alone): as separate launches 0 / 1 / 2 / 4 / 8 passes =
+// 170 / 167 / 165 / 172 / 197 us and 408 / 373 / 358 / 347 / 358 us (profiles/r02a_ab_experimental.txt); in-kernel iterations: DESIGN.md 4.5.
+__global__ void __launch_bounds__(128) view_refit_kernel(ViewNode *v, long long n_inner, int iters)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_inner) return;
@@ -168,22 +170,31 @@ __global__ void __launch_bounds__(128) view_refit_kernel(ViewNode *v, long long 
     float4 r[2] = {__ldcg(me), __ldcg(me + 1)};
     float4 zc = __ldcg(me + 2);
     const int child[2] = {__float_as_int(zc.z), __float_as_int(zc.w)};
+    if (child[0] < 0 && child[1] < 0) return; // two leaves: already the triangles' rectangles
     float z[2] = {zc.x, zc.y};
+    for (int it = 0; it < iters; ++it) {
+        bool changed = false;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (child[c] < 0) continue; // a leaf: already the triangle's rectangle
-        const float4 *cp = reinterpret_cast<const float4 *>(v + child[c]);
-        const float4 a = __ldcg(cp), b = __ldcg(cp + 1), cz = __ldcg(cp + 2);
-        // fminf / fmaxf drop NaN; an empty rectangle is (inf, -inf, inf, -inf) and an unbounded one (-inf, inf, -inf, inf)
-        r[c].x = fmaxf(r[c].x, fminf(a.x, b.x)); r[c].y = fminf(r[c].y, fmaxf(a.y, b.y));
-        r[c].z = fmaxf(r[c].z, fminf(a.z, b.z)); r[c].w = fminf(r[c].w, fmaxf(a.w, b.w));
-        z[c] = fmaxf(z[c], fminf(cz.x, cz.y));
+        for (int c = 0; c < 2; ++c) {
+            if (child[c] < 0) continue; // a leaf: already the triangle's rectangle
+            const float4 *cp = reinterpret_cast<const float4 *>(v + child[c]);
+            const float4 a = __ldcg(cp), b = __ldcg(cp + 1), cz = __ldcg(cp + 2);
+            // fminf / fmaxf drop NaN; an empty rectangle is (inf, -inf, inf, -inf) and an unbounded one (-inf, inf, -inf, inf)
+            const float4 o = r[c];
+            const float oz = z[c];
+            r[c].x = fmaxf(o.x, fminf(a.x, b.x)); r[c].y = fminf(o.y, fmaxf(a.y, b.y));
+            r[c].z = fmaxf(o.z, fminf(a.z, b.z)); r[c].w = fminf(o.w, fmaxf(a.w, b.w));
+            z[c] = fmaxf(oz, fminf(cz.x, cz.y));
+            changed = changed || r[c].x != o.x || r[c].y != o.y || r[c].z != o.z || r[c].w != o.w || z[c] != oz;
+        }
+        if (changed) {
+            __stcg(me, r[0]); __stcg(me + 1, r[1]);
+            __stcg(me + 2, make_float4(z[0], z[1], zc.z, zc.w));
+        }
     }
-    me[0] = r[0]; me[1] = r[1];
-    me[2] = make_float4(z[0], z[1], zc.z, zc.w);
 }
 
-int g_view_refit_passes = 2; // rt_raycast_set_view_refit; 2 measured best on B200 for both the cfg4 orbit (+4.6 %) and the frame-filling camera (-14 % frame time), profiles/r02c_*
+int g_view_refit_passes = 4; // rt_raycast_set_view_refit; 4 iterations measured best on B200 for the cfg4 orbit (76.2 against 70.9 Grays/s without), 8 for the frame-filling camera
 
 struct TraceArgs {
     const RtBvhNode *nodes;
@@ -626,9 +637,10 @@ int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triang
             p.tris = a.tris; // leaf rectangles from the triangles themselves (189 -> 169 us per cfg4 frame against box rectangles)
             project_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
             RT_CUDA(cudaGetLastError());
-            for (int k = 0; k < g_view_refit_passes; ++k) // experimental, 0 by default
-                view_refit_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p.vnodes, p.n_inner);
-            RT_CUDA(cudaGetLastError());
+            if (g_view_refit_passes > 0) {
+                view_refit_kernel<<<(unsigned)((p.n_inner + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p.vnodes, p.n_inner, g_view_refit_passes);
+                RT_CUDA(cudaGetLastError());
+            }
             a.vnodes = p.vnodes;
         }
     }
@@ -739,8 +751,8 @@ int rt_raycast_screen_bounds(const float *camera, const double *lo, const double
     return 1;
 }
 
-// EXPERIMENTAL (see view_refit_kernel): number of tightening passes rt_raycast_primary runs after the projection, 0..64.
-// Process-wide; 0 (the default) leaves the measured path exactly as it is.
+// Number of tightening iterations (inside one launch of view_refit_kernel) rt_raycast_primary runs after the projection, 0..64.
+// Process-wide.
 int rt_raycast_set_view_refit(int passes)
 {
     RT_REQUIRE(passes >= 0 && passes <= 64, "0..64 passes");

@@ -14,7 +14,8 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 os.makedirs("profiles", exist_ok=True)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# rep: an .ncu-rep, or the CSV `ncu -i rep --page raw --csv` printed (so the summaries can be redone without the report)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
@@ -51,7 +52,7 @@ WANT = [
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % (should be 0)"),
-    ("sm__inst_executed.sum", "warp instructions"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / warp instr"),
+    ("smsp__inst_executed.sum", "warp instructions"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / warp instr"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"), ("sm__maximum_warps_per_active_cycle_pct", "theoretical occupancy %"),
     ("sm__inst_executed.avg.per_cycle_active", "IPC (active)"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / scheduler"),
@@ -87,11 +88,11 @@ for name, rs in launches.items():
     lines.append(f"{'DRAM traffic per launch (read+write)':42s} {traffic / 1e6:.2f} MB")
     lines.append(f"{'all launches of this kernel, us':42s} " + " ".join(f"{num(r, 'gpu__time_duration.sum'):.1f}" for r in rs))
     open(f"profiles/{tag}_{fname}.txt", "w").write("\n".join(lines) + "\n")
-    facts[name] = {"dram_bytes_per_launch": traffic, "warp_instructions": num(best, "sm__inst_executed.sum"),
+    facts[name] = {"dram_bytes_per_launch": traffic, "warp_instructions": num(best, "smsp__inst_executed.sum"),
                    "issue_slots_busy_pct": num(best, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    "duration_us": num(best, "gpu__time_duration.sum"), "launches": len(rs), "all": rs}
     table.append((name, len(rs), num(best, "gpu__time_duration.sum"), best[col["launch__registers_per_thread"]], num(best, "sm__warps_active.avg.pct_of_peak_sustained_active"),
-                  num(best, "smsp__issue_active.avg.pct_of_peak_sustained_active"), num(best, "sm__inst_executed.sum"), traffic / 1e6,
+                  num(best, "smsp__issue_active.avg.pct_of_peak_sustained_active"), num(best, "smsp__inst_executed.sum"), traffic / 1e6,
                   num(best, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), num(best, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
                   num(best, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")))
 with open(f"profiles/{tag}_inventory.txt", "w") as fh:
@@ -108,7 +109,7 @@ def pick(pattern, nth=-1):
     for name, f in facts.items():
         if re.search(pattern, name):
             r = f["all"][nth]
-            return {"dram": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"), "instr": num(r, "sm__inst_executed.sum"),
+            return {"dram": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"), "instr": num(r, "smsp__inst_executed.sum"),
                     "issue": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), "us": num(r, "gpu__time_duration.sum")}
     return None
 
@@ -118,7 +119,7 @@ out = {}
 ray = [f for f in (pick(r"^project_kernel", 0), pick(r"^raycast_kernel<8, 0, 0, 1>", 0)) if f]
 refit = facts.get(next((n for n in facts if n.startswith("view_refit_kernel")), ""), None)
 if len(ray) == 2:
-    extra = [{"dram": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"), "instr": num(r, "sm__inst_executed.sum"), "us": num(r, "gpu__time_duration.sum")}
+    extra = [{"dram": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"), "instr": num(r, "smsp__inst_executed.sum"), "us": num(r, "gpu__time_duration.sum")}
              for r in (refit["all"][0:2] if refit else [])]
     out["raycast_frame"] = {"dram_bytes_per_launch": sum(f["dram"] for f in ray + extra), "warp_instructions_per_frame": sum(f["instr"] for f in ray + extra),
                             "issue_slots_busy_pct": ray[1]["issue"], "us_serialised": sum(f["us"] for f in ray + extra),

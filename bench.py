@@ -638,7 +638,7 @@ def bench_tiles(args, rank, world, rows, vb):
     import torch
     import rendering as ren
     from rendering._raycaster import Raycaster
-    from rendertoy_b200 import lessons, parallel
+    from rendertoy_b200 import lessons, parallel, _native
 
     C = max(1, args.commit_every)
     ring = 2 * C * SUB                                  # frames in the ring
@@ -660,6 +660,8 @@ def bench_tiles(args, rank, world, rows, vb):
             return ren.Image(W, H, ren._core.RGBA, memory=store.frame(i)) if in_store else ren.create_image2d(W, H, ren._core.RGBA)
         if path == "raycast":
             rc = Raycaster([ren.Mesh(vb, None)])
+            if args.tiles_view_refit is not None:
+                _native.call("rt_raycast_set_view_refit", args.tiles_view_refit)
             targets = [image(i) for i in range(n_targets)]
             streams = Streams(args.raycast_streams)
 
@@ -742,6 +744,8 @@ def bench_tiles(args, rank, world, rows, vb):
                                       "ranks != 0 render locally and push their stripes with one 3-D copy-engine transfer (content rect only), rank 0 in place")
                                    + f"; commit (4-byte all-reduce) every {C * SUB} frames")}
         del targets
+        if path == "raycast":
+            _native.call("rt_raycast_set_view_refit", args.view_refit)
         if store is not None:
             torch.cuda.synchronize()
             barrier_sync(world)
@@ -983,6 +987,7 @@ def main():
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
                          "IPC-mapped frame store while the next frames trace; peer = the kernels store straight into that frame store "
                          "over NVLink (fused); nccl = send/recv gather")
+    ap.add_argument("--tiles-view-refit", type=int, default=None, help="tile partition: view-node tightening iterations (default: as --view-refit)")
     ap.add_argument("--tiles-gather", default="auto", choices=["auto", "peer", "copy"],
                     help="N>1, tile partition: how stripes reach rank 0's frame; auto = copy for ray-cast frames, peer for raster frames "
                          "(measured at N=2 and 8: 123/174 vs 108/149 Grays/s, 2120/2731 vs 1392/1349 Mtris/s)")

@@ -120,10 +120,10 @@ ray = [f for f in (pick(r"^project_kernel", 0), pick(r"^raycast_kernel<8, 0, 0, 
 refit = facts.get(next((n for n in facts if n.startswith("view_refit_kernel")), ""), None)
 if len(ray) == 2:
     extra = [{"dram": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"), "instr": num(r, "smsp__inst_executed.sum"), "us": num(r, "gpu__time_duration.sum")}
-             for r in (refit["all"][0:2] if refit else [])]
+             for r in (refit["all"][0:1] if refit else [])]
     out["raycast_frame"] = {"dram_bytes_per_launch": sum(f["dram"] for f in ray + extra), "warp_instructions_per_frame": sum(f["instr"] for f in ray + extra),
                             "issue_slots_busy_pct": ray[1]["issue"], "us_serialised": sum(f["us"] for f in ray + extra),
-                            "source": f"profiles/{tag}_inventory.txt: project_kernel + {len(extra)} view_refit_kernel + raycast_kernel<8> of the cfg4 frame (lesson06 camera, t = 0.5)"}
+                            "source": f"profiles/{tag}_inventory.txt: project_kernel + view_refit_kernel ({len(extra)} launch) + raycast_kernel<8> of the cfg4 frame (lesson06 camera, t = 0.5)"}
 ras = [pick(r"^fill_u64_kernel", 0), pick(r"^raster_kernel<8, 0>", 0), pick(r"^coverage_kernel<8, 0>", 0), pick(r"^resolve_kernel<8>", 0)]
 if all(ras):
     out["raster_frame"] = {"dram_bytes_per_launch": sum(f["dram"] for f in ras), "warp_instructions_per_frame": sum(f["instr"] for f in ras),

@@ -245,7 +245,7 @@ class FrameLoop:
     The store is a ring of 2 * commit_every sub-batches (SUB frames per rank each); a stream-ordered 4-byte all-reduce every
     `commit_every` sub-batches tells rank 0 those frames are complete, and a slot is rewritten only two commits later."""
 
-    def __init__(self, ren, world, rank, W, H, frames, gather, commit_every, n_streams, make_target):
+    def __init__(self, ren, world, rank, W, H, frames, gather, commit_every, n_streams, make_target, tile_push=False):
         import torch
         from rendertoy_b200 import parallel
         self.torch, self.ren, self.world, self.rank, self.W, self.H, self.frames = torch, ren, world, rank, W, H, frames
@@ -270,6 +270,7 @@ class FrameLoop:
         self.rendered_ev = [torch.cuda.Event() for _ in range(SUB)]
         self.pushed_ev = [torch.cuda.Event() for _ in range(SUB)]
         self.pushed_bytes = 0
+        self.tile_push = tile_push      # gather == "copy": rt_push_tiles (a kernel, non-clear 32x32 tiles) instead of rt_copy_rect (copy engine, content rect)
         self.q = 0                                      # global sub-batch counter
         if self.gather == "nccl":
             self.local = torch.empty((SUB, H, W), dtype=torch.int32, device="cuda")
@@ -298,7 +299,10 @@ class FrameLoop:
                 if self.push_stream is not None:
                     self.rendered_ev[j].record(st)
                     self.push_stream.wait_event(self.rendered_ev[j])
-                    self.pushed_bytes += self.store.push(self.slot(q, j), tgt_ptr(tgt), content if sparse else full, self.push_stream.cuda_stream)
+                    if self.tile_push:
+                        self.store.push_tiles(self.slot(q, j), tgt_ptr(tgt), self.push_stream.cuda_stream)
+                    else:
+                        self.pushed_bytes += self.store.push(self.slot(q, j), tgt_ptr(tgt), content if sparse else full, self.push_stream.cuda_stream)
                     self.pushed_ev[j].record(self.push_stream)
                     self.pushed[j] = self.pushed_ev[j]
             self.q += 1
@@ -347,6 +351,11 @@ def tgt_tensor(t):
 def gather_text(loop, sparse):
     if loop.world == 1:
         return "single GPU, no gather"
+    if loop.gather == "copy" and loop.tile_push:
+        return ("ranks != 0 render locally and a small kernel on the producing GPU (rt_push_tiles) stores the 32x32-pixel tiles of each finished frame "
+                "that hold something other than the clear colour -- or did the last time the slot was written -- straight into rank 0's frame store "
+                "(CUDA IPC peer memory, cleared at start) while the next frames render; rank 0 renders in place; "
+                f"frame store = ring of {loop.ring} sub-batches x {SUB} frames per rank, one stream-ordered 4-byte all-reduce per {loop.C} sub-batches")
     ring = f"frame store = ring of {loop.ring} sub-batches x {SUB} frames per rank, one stream-ordered 4-byte all-reduce per {loop.C} sub-batches"
     if loop.gather == "peer":
         return "every rank's kernel stores its pixels straight into rank 0's frame store over NVLink (CUDA IPC peer memory); " + ring
@@ -529,18 +538,22 @@ def bench_raster(args, rank, world, rows, vb, W=RAS_W, H=RAS_H, frames=None, ful
         img = ren.Image(W, H, ren._core.RGBA, memory=mem) if mem is not None else ren.create_presenter(W, H).get_render_target()
         return lessons.build_lesson08(ren, img)          # (raster, globals)
 
-    loop = FrameLoop(ren, world, rank, W, H, F, args.raster_gather, args.commit_every, SUB if args.raster_streams else 1, make_target)
+    loop = FrameLoop(ren, world, rank, W, H, F, args.raster_gather, args.commit_every, SUB if args.raster_streams else 1, make_target,
+                     tile_push=args.raster_push == "tiles")
     for k in range(ORBIT):
         raster_camera(ren, k, W, H)
 
     def render(i, k, tgt):
         tgt[0].draw_frame(vb, None, raster_camera(ren, k, W, H))      # = set World/View/Proj + clear + clear + draw_triangles
-        return tgt[0].content_rect if loop.push_stream is not None else None
+        return tgt[0].content_rect if (loop.push_stream is not None and not loop.tile_push) else None
 
     for s in range(args.warmup):
         loop.step(s, render, args.sparse)
     barrier_sync(world)
     loop.pushed_bytes = 0
+    if loop.store is not None and loop.store.tile_bytes is not None:
+        loop.store.tile_bytes.zero_()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
@@ -553,8 +566,12 @@ def bench_raster(args, rank, world, rows, vb, W=RAS_W, H=RAS_H, frames=None, ful
     ms = max(ms_ranks)
     value = n_tris * F * world * args.steps / (ms * 1e-3) / 1e6
     frame_ms = e0.elapsed_time(e1) / (args.steps * F)
+    if loop.store is not None and loop.store.tile_bytes is not None:
+        loop.pushed_bytes = int(loop.store.tile_bytes.item())
+    push_bytes_step = all_ranks(loop.pushed_bytes / max(args.steps, 1), world)
     out = {"value": value, "ms": ms, "ms_ranks": ms_ranks, "frame_ms": frame_ms, "frames": F, "gather": gather_text(loop, args.sparse),
-           "gather_verified": gather_ok, "launches": 4 * F * args.steps, "streams": max(1, len(loop.streams.streams))}
+           "gather_verified": gather_ok, "launches": (4 + (1 if (loop.tile_push and loop.push_stream is not None) else 0)) * F * args.steps,
+           "streams": max(1, len(loop.streams.streams)), "push_bytes_step": push_bytes_step}
     if not full:
         loop.close()
         return out
@@ -951,7 +968,10 @@ def assemble_ras(args, world, r):
         "metric": METRIC_RAS, "value": r["value"], "unit": "Mtris/s", "ms_per_step": r["ms"] / args.steps, "scaling": "weak", "config": CONFIG_RAS,
         "run": {"frames_per_rank_per_step": r["frames"], "partition": "frames k = rank (mod N); " + r["gather"],
                 "l2": f"{SUB} independent raster targets per rank (~300 MB of key/colour/record buffers > L2)",
-                "streams": f"one CUDA stream per frame target ({r['streams']})", "timed_region_ms_per_rank": r["ms_ranks"]},
+                "streams": f"one CUDA stream per frame target ({r['streams']})", "timed_region_ms_per_rank": r["ms_ranks"],
+                **({"gather_verified": "every rank's locally rendered frames of the last sub-batch == its slots of rank 0's frame store, bit for bit",
+                    "gather_bytes_per_step_per_rank": r["push_bytes_step"], "full_frame_bytes_per_step_per_rank": 4 * RAS_W * RAS_H * r["frames"]}
+                   if r["gather_verified"] else {})},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": facts.get("dram_bytes_per_launch"),
                      "peak_source": peak_src, "unit_of_work": "one frame = 4 kernels (depth clear, raster_kernel, "
@@ -980,6 +1000,9 @@ def main():
     ap.add_argument("--dense-readback", dest="sparse_readback", action="store_false",
                     help="e2e: read whole frames back instead of the rect that can differ from the clear colour")
     ap.add_argument("--view-refit", type=int, default=None, help="tightening passes over the screen-space nodes (rt_raycast_set_view_refit)")
+    ap.add_argument("--raster-push", default="tiles", choices=["tiles", "rect"],
+                    help="--raster-gather copy: tiles = rt_push_tiles (kernel on the producer, non-clear 32x32 tiles); rect = rt_copy_rect "
+                         "(copy engine, Raster.content_rect)")
     ap.add_argument("--raster-gather", default="copy", choices=["peer", "copy", "nccl"],
                     help="N>1, raster frames: copy = render locally, push Raster.content_rect with the copy engine; peer = the kernels "
                          "store into rank 0's frame store")

@@ -220,6 +220,15 @@ int rt_peer_close(void *d_ptr);
  * pointer may be local device, peer-mapped device or pinned host memory. */
 int rt_copy_rect(void *d_dst, int64_t dst_pitch_bytes, const void *d_src, int64_t src_pitch_bytes, int64_t width_bytes,
                       int64_t rows, void *stream);
+/* Sparse push by 32x32-pixel tiles, for frames that are mostly content (a frame-filling raster view: bounding rect ~90 % of
+ * the frame, covered pixels a third): a kernel on the producing GPU stores only the tiles that hold a pixel != clear_px, or held
+ * one the last time this producer pushed into the same destination (d_tile_state: rt_push_tiles_state_bytes(w, h) bytes of
+ * producer-local device memory per destination frame, zero-filled when the destination is known to be all clear_px), into the
+ * frame at d_dst (same W x H BGRA8 layout; rank 0's peer-mapped slot).  Afterwards the destination equals the source.  width
+ * must be a multiple of 4.  d_bytes: NULL, or a device uint64 the kernel adds the bytes it stored to. */
+int64_t rt_push_tiles_state_bytes(int width, int height);
+int rt_push_tiles(void *d_dst, const void *d_src, int width, int height, uint32_t clear_px, void *d_tile_state, void *d_bytes,
+                  void *stream);
 /* The gather of the image-space partition: move the row stripes a rank owns -- rows y in [y0, y1] with
  * (y / stripe_rows) % mod == rem, bytes [x_bytes, x_bytes + width_bytes) of each row -- from the frame at d_src to the same
  * place in the frame at d_dst (same row pitch; local, peer-mapped or pinned host memory).  One 3-D copy-engine transfer for

@@ -54,6 +54,8 @@ SIGNATURES = {
     "rt_peer_open": (C.c_int, [_VP, C.POINTER(_VP)]),
     "rt_peer_close": (C.c_int, [_VP]),
     "rt_copy_rect": (C.c_int, [_VP, _I64, _VP, _I64, _I64, _I64, _VP]),
+    "rt_push_tiles_state_bytes": (_I64, [_I32, _I32]),
+    "rt_push_tiles": (C.c_int, [_VP, _VP, _I32, _I32, _U32, _VP, _VP, _VP]),
     "rt_copy_stripes": (C.c_int, [_VP, _VP, _I64, _I64, _I64, _I64, _I64, _I32, _I32, _I32, _VP]),
     "rt_raster_points_scratch_bytes": (_I64, [_I64]),
     "rt_raster_draw_points": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, C.POINTER(C.c_int), _VP]),

@@ -284,3 +284,32 @@ def test_draw_frame_equals_the_four_tutorial_calls(ren, oracle):
         assert np.array_equal(b.get_render_target().get(), ref.bgra)
         b.draw_frame(vb, None)                                                  # same matrices, from the buffer
         assert np.array_equal(b.get_render_target().get(), ref.bgra)
+
+
+def test_frame_store_tile_push(ren):
+    """FrameStore.push_tiles (rt_push_tiles): an orbit of raster frames cycling through two slots of a cleared store; after
+    every push the slot equals the frame bit for bit although only the non-clear 32x32 tiles (and the ones that were non-clear
+    in the slot before) were stored; a frame size that is not a multiple of the tile exercises the partial tiles."""
+    import torch
+    from rendertoy_b200 import parallel
+    for w, h, lo_frac in ((1920, 1080, 0.75), (500, 333, 0.95)):
+        rows = scenes.dragon(20_000)
+        vb = _upload(ren, rows)
+        raster, g = lessons.build_lesson08(ren, ren.create_presenter(w, h).get_render_target())
+        store = parallel.FrameStore(2, w, h)
+        assert store.ok
+        try:
+            side = torch.cuda.Stream()
+            for k in range(10):
+                lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8 if k % 3 else 6, 0.6 * k, w, h))
+                lessons.render_frame(ren, raster, vb)
+                side.wait_stream(torch.cuda.current_stream())
+                store.push_tiles(k % 2, raster.get_render_target().ptr, side.cuda_stream)
+                torch.cuda.current_stream().wait_stream(side)
+                frame = raster.get_render_target().buffer.tensor().view(torch.int32).view(h, w)
+                assert torch.equal(store.frames()[k % 2], frame), f"slot differs from frame {k}"
+                assert frame.any()
+            moved = int(store.tile_bytes.item())
+            assert 0 < moved < lo_frac * 10 * ((w + 31) // 32) * ((h + 31) // 32) * 4096, moved
+        finally:
+            store.close()

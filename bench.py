@@ -677,10 +677,13 @@ def bench_tiles(args, rank, world, rows, vb):
             return ren.Image(W, H, ren._core.RGBA, memory=store.frame(i)) if in_store else ren.create_image2d(W, H, ren._core.RGBA)
         if path == "raycast":
             rc = Raycaster([ren.Mesh(vb, None)])
-            if args.tiles_view_refit is not None:
-                _native.call("rt_raycast_set_view_refit", args.tiles_view_refit)
+            # every rank repeats the projection + tightening of the whole BVH for every frame: from 4 ranks up two iterations pay
+            # better than four, and more streams hide more of those single-wave kernels (measured at N = 8 with graph replay:
+            # 4 streams / 4 iterations 255 Grays/s, 8 / 4 -> 301, 8 / 2 -> 318, 2 / 4 -> 168)
+            tiles_refit = args.tiles_view_refit if args.tiles_view_refit is not None else (2 if world >= 4 else args.view_refit)
+            _native.call("rt_raycast_set_view_refit", tiles_refit)
             targets = [image(i) for i in range(n_targets)]
-            streams = Streams(args.raycast_streams)
+            streams = Streams(max(args.raycast_streams, SUB) if world > 1 else args.raycast_streams)
 
             def render(f, tgt):
                 return rc.render(tgt, ray_camera(ren, f), stripes=stripes)
@@ -696,32 +699,72 @@ def bench_tiles(args, rank, world, rows, vb):
             def render(f, tgt):
                 tgt[0].draw_frame(vb, None, raster_camera(ren, f))
                 return tgt[0].content_rect if push_stream is not None else None
-        pushed = [None] * SUB
-        counter = [0]
+        L = C * SUB                                     # frames between two commits
+        assert FT % L == 0 and FT % ring == 0 and FT % ORBIT == 0, "a step is whole orbits, whole commit intervals, whole rings"
+        rendered_ev = [torch.cuda.Event() for _ in range(SUB)]
+        pushed_ev = [torch.cuda.Event() for _ in range(SUB)]
 
-        def step():
+        def interval(f0):
+            """enqueue frames f0 .. f0 + L - 1 of the orbit (slot f % ring, local target f % SUB); self-contained: forks from and
+            joins into the current main stream, waits only on events recorded inside itself (so it can be captured as a graph)"""
+            pushed = [False] * SUB
             streams.fork()
-            for _ in range(FT):
-                f = counter[0]
+            for f in range(f0, f0 + L):
                 st = streams.use(f)
                 j = f % SUB
-                if push_stream is not None and pushed[j] is not None:
-                    st.wait_event(pushed[j])
+                if push_stream is not None and pushed[j]:
+                    st.wait_event(pushed_ev[j])                # the local target's previous frame has left
                 tgt = targets[f % ring] if in_store else targets[j]
                 content = render(f, tgt)
                 if push_stream is not None:
-                    ev = torch.cuda.Event(); ev.record(st)
-                    push_stream.wait_event(ev)
+                    rendered_ev[j].record(st)
+                    push_stream.wait_event(rendered_ev[j])
                     store.push_stripes(f % ring, tgt_ptr(tgt), content, stripes, push_stream.cuda_stream)
-                    done = torch.cuda.Event(); done.record(push_stream)
-                    pushed[j] = done
-                counter[0] += 1
-                if store is not None and counter[0] % (C * SUB) == 0:
-                    streams.join(*([push_stream] if push_stream is not None else []))
-                    store.commit()
-                    streams.fork()
+                    pushed_ev[j].record(push_stream)
+                    pushed[j] = True
             streams.join(*([push_stream] if push_stream is not None else []))
 
+        graphs = None
+
+        def step():
+            for g in range(FT // L):
+                if graphs is not None:
+                    graphs[g % len(graphs)].replay()
+                else:
+                    interval(g * L)
+                if store is not None:
+                    store.commit()
+
+        for _ in range(2):                                  # eager: allocations, and the slots' content history reaches its steady state
+            step()
+        barrier_sync(world)
+        graph_note = "eager launches from Python"
+        if args.tiles_graphs:
+            # The orbit is a fixed launch sequence (256 cameras, ring slots f % ring): capture each commit interval ONCE as a CUDA
+            # graph -- kernels with their baked camera / matrices, the copy-engine pushes, the stream forks and joins -- and replay.
+            # The per-frame host cost (Python + ~4 driver calls, ~40 us: the plateau of the eager loop from N = 4 on) disappears.
+            try:
+                main_stream = streams.main
+                cap = torch.cuda.Stream()
+                caught = []
+                for g in range(ORBIT // L):
+                    cg = torch.cuda.CUDAGraph()
+                    cap.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.graph(cg, stream=cap):
+                        streams.main = torch.cuda.current_stream()
+                        interval(g * L)
+                    streams.main = main_stream
+                    caught.append(cg)
+                graphs = caught
+                graph_note = f"CUDA-graph replay: the orbit's {ORBIT // L} commit intervals of {L} frames captured once (kernels, pushes, stream forks/joins), one cudaGraphLaunch each"
+            except Exception as e:      # e.g. a driver that refuses peer copies inside a capture: stay eager, and say so
+                streams.main = main_stream
+                torch.cuda.set_stream(main_stream)
+                graphs = None
+                graph_note = f"eager launches from Python (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        captured = all_ok(graphs is not None, world)
+        if not captured:
+            graphs = None
         for _ in range(max(1, min(args.warmup, 3))):
             step()
         barrier_sync(world)
@@ -731,6 +774,7 @@ def bench_tiles(args, rank, world, rows, vb):
             step()
         e1.record()
         barrier_sync(world)
+        counter = [FT]
         ms_ranks = all_ranks(e0.elapsed_time(e1), world)
         ms = max(ms_ranks)
         # untimed check on rank 0: the gathered frame of the last step equals a whole-frame render of the same camera
@@ -754,7 +798,8 @@ def bench_tiles(args, rank, world, rows, vb):
         res[path] = {"metric": METRIC_RAY if path == "raycast" else METRIC_RAS, "unit": "Mrays/s" if path == "raycast" else "Mtris/s",
                      "value": units * FT * args.steps / (ms * 1e-3) / 1e6, "scaling": "strong", "n_gpus": world,
                      "ms_per_frame": ms / (FT * args.steps), "frames_per_step": FT, "timed_region_ms_per_rank": ms_ranks,
-                     "gathered_frame_verified": ok if world > 1 else None,
+                     "gathered_frame_verified": ok if world > 1 else None, "launch": graph_note,
+                     "streams": max(1, len(streams.streams)), **({"view_refit_iterations": tiles_refit} if path == "raycast" else {}),
                      "partition": ("single GPU: the whole frame, no stripes" if world == 1 else
                                    f"every frame split into row stripes of {parallel.BAND} rows, stripe s -> rank s % {world}; one launch per rank and frame; "
                                    + ("kernels store their stripes straight into rank 0's frame (peer memory)" if gather == "peer" else
@@ -768,8 +813,9 @@ def bench_tiles(args, rank, world, rows, vb):
             barrier_sync(world)
             store.close()
     res["note"] = ("configs[3] as BASELINE.json words it (image-space tiles of one 4K frame over N GPUs + gather), beside the frames partition of the "
-                   "primary line.  What does not shrink with N: the per-frame projection of the BVH (ray cast) resp. vertex shading + setup of all "
-                   "triangles (raster) are replicated on every rank, plus one launch sequence per rank and frame.")
+                   "primary line.  What does not shrink with N: the per-frame projection + tightening of the BVH (ray cast) resp. vertex shading + "
+                   "setup of all triangles (raster) are replicated on every rank.  The orbit is replayed as CUDA graphs: launched eagerly from Python "
+                   "the loop is host-bound from N = 4 on (~40 us of Python and driver calls per frame).")
     return res
 
 
@@ -1027,6 +1073,7 @@ def main():
                     help="N>1, raycast frames: copy = ranks render locally and a copy engine pushes each finished frame into rank 0's "
                          "IPC-mapped frame store while the next frames trace; peer = the kernels store straight into that frame store "
                          "over NVLink (fused); nccl = send/recv gather")
+    ap.add_argument("--tiles-graphs", type=int, default=1, help="tile partition: 1 = replay the orbit as CUDA graphs (default), 0 = eager launches from Python")
     ap.add_argument("--tiles-view-refit", type=int, default=None, help="tile partition: view-node tightening iterations (default: as --view-refit)")
     ap.add_argument("--tiles-gather", default="auto", choices=["auto", "peer", "copy"],
                     help="N>1, tile partition: how stripes reach rank 0's frame; auto = copy for ray-cast frames, peer for raster frames "
@@ -1064,7 +1111,7 @@ def main():
     if want("config4") and not args.no_config4:
         cfg4 = bench_config4(args, rank, world, rows)
     if rank == 0:
-        if not args.no_cpu_baseline and args.only is None:
+        if not args.no_cpu_baseline and args.only is None and world == 1:     # the CPU legs belong to the N = 1 line
             import oracle
             oracle.build()
             cores = cpu_threads()

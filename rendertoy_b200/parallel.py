@@ -241,7 +241,7 @@ class FrameStore:
         if self._copier is None:
             self._copier = SparseFrameCopier(self.width, self.height)
         c = self._copier
-        key = ("stripes", k)
+        key = ("stripes", k, tuple(stripes))
         r = cover_rect(c._content.get(key), content, self.width, self.height)
         c._content[key] = content
         if r is None:

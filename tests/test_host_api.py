@@ -499,3 +499,33 @@ def test_raster_refuses_a_render_target_it_cannot_write(ren):
     from rendertoy_b200 import lessons
     with pytest.raises(AssertionError):
         lessons.build_lesson08(ren, ren.create_image2d(8, 8, ren.float4))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: one JSON line on stdout with the contract's keys, the SAME `config` dict our arm prints, all
+    host cores used whatever OMP_NUM_THREADS says (torchrun exports 1), and nothing under rendertoy_b200/ imports the oracle."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--path", "raster", "--steps", "2", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["config"] == bench.CONFIG_RAS and d["metric"] == bench.METRIC_RAS and d["unit"] == "Mtris/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "cpu_baseline", "e2e"):
+        assert key in d
+    ncpu = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncpu and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0
+    for dirpath, _, files in os.walk(os.path.join(root, "rendertoy_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"

@@ -488,3 +488,35 @@ def test_stripe_partition_equals_the_whole_frame(ren, w, h, n_tris, world, lesso
     assert torch.equal(parts.buffer.tensor(), whole.buffer.tensor()), "striped frame differs from the whole frame"
     assert torch.equal(hits_parts.view(torch.int32), hits_whole.view(torch.int32)), "striped hit records differ"
     assert (whole.get()[:, :, 3] != 0).any()
+
+
+@pytest.mark.parametrize("w,h,world", [(3840, 2160, 8), (1920, 1080, 3), (500, 333, 2)])
+def test_frame_store_stripe_push(ren, w, h, world):
+    """FrameStore.push_stripes (rt_copy_stripes: one 3-D copy-engine transfer for a rank's whole stripes + 2-D ones for cut
+    stripes): every "rank" pushes its stripes of an orbit of locally rendered frames into the same two slots; after all ranks
+    pushed, the slot equals the frame bit for bit although only the cover rect travelled; a rank's push must not write foreign rows."""
+    from rendering._raycaster import Raycaster
+    from rendertoy_b200 import parallel
+    rows = scenes.dragon(20_000)
+    rc = Raycaster([ren.Mesh(_mesh_buffer(ren, rows), None)])
+    store = parallel.FrameStore(2, w, h)       # push_stripes keeps the slot's previous content rect per (slot, stripes)
+    assert store.ok
+    try:
+        local = ren.create_image2d(w, h, ren._core.RGBA)
+        side = torch.cuda.Stream()
+        yy = torch.arange(h, device="cuda")
+        for k in range(6):
+            cam = _camera(ren, 6 if k % 3 else 8, 0.45 * k, w, h)
+            content = rc.render(local, cam)
+            frame = local.buffer.tensor().view(torch.int32).view(h, w)
+            side.wait_stream(torch.cuda.current_stream())
+            for rank in range(world):
+                before = store.frames()[k % 2].clone()
+                store.push_stripes(k % 2, local.ptr, content, (parallel.BAND, world, rank), side.cuda_stream)
+                side.synchronize()
+                foreign = (yy // parallel.BAND) % world != rank
+                assert torch.equal(store.frames()[k % 2][foreign], before[foreign]), f"rank {rank} wrote foreign rows"
+            assert torch.equal(store.frames()[k % 2], frame), f"slot differs from frame {k}"
+            assert frame.any()
+    finally:
+        store.close()

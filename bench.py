@@ -668,7 +668,7 @@ def bench_tiles(args, rank, world, rows, vb):
         store = parallel.FrameStore(ring, W, H) if world > 1 else None
         if store is not None and not store.ok:
             raise SystemExit("tile partition needs the IPC frame store")
-        stripes = (parallel.BAND, world, rank) if world > 1 else None
+        stripes = parallel.stripes_of(rank, world) if world > 1 else None
         in_store = store is not None and (gather == "peer" or rank == 0)
         push_stream = torch.cuda.Stream() if (gather == "copy" and rank != 0) else None
         n_targets = ring if in_store else SUB

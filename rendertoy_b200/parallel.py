@@ -21,6 +21,12 @@ import torch.distributed as dist
 BAND = 64  # rows per band: multiple of the traversal's 8x4 warp tile, small enough to balance a frame
 
 
+def stripes_of(rank: int, world: int, band: int = BAND) -> Tuple[int, int, int]:
+    """(rows, mod, rem): the same partition as tile_rects() in the form Raster.set_scissor(stripes=) and
+    Raycaster.render(stripes=) take -- one launch per rank and frame instead of one per band."""
+    return (band, world, rank)
+
+
 def tile_rects(width: int, height: int, rank: int, world: int, band: int = BAND) -> List[Tuple[int, int, int, int]]:
     """(x0, y0, w, h) row bands owned by `rank`: band b belongs to rank b % world.  Bands interleave so every
     rank sees a similar mix of background and mesh."""
@@ -137,6 +143,24 @@ class SparseFrameCopier:
         self.bytes_moved += n
         return n
 
+    def copy_stripes(self, key, dst_ptr, src_ptr, content, stripes, stream):
+        """The same for ONE rank's share of a frame that several ranks write (image-space partition): of the cover rect only the
+        rows of the stripes (rows, mod, rem) -- stripe s = y // rows is this rank's iff s % mod == rem -- travel, as one 3-D
+        copy-engine transfer (rt_copy_stripes).  dst_ptr / src_ptr: the two full frames (same layout).  Every rank keeps the
+        destination's content history for its own stripes, keyed by (key, stripes)."""
+        key = ("stripes", key, tuple(stripes))
+        r = cover_rect(self._content.get(key), content, self.width, self.height)
+        self._content[key] = content
+        if r is None:
+            return 0
+        x0, y0, x1, y1 = r
+        rows, mod, rem = stripes
+        self._native.call("rt_copy_stripes", dst_ptr, src_ptr, 4 * self.width, 4 * x0, 4 * (x1 - x0 + 1), y0, y1, rows, mod, rem, stream)
+        n = 4 * (x1 - x0 + 1) * sum(min(y1, (s + 1) * rows - 1) - max(y0, s * rows) + 1
+                                    for s in range(y0 // rows, y1 // rows + 1) if s % mod == rem)
+        self.bytes_moved += n
+        return n
+
 
 class _RawDeviceMemory:
     """Adapter exposing a raw device address to torch through __cuda_array_interface__."""
@@ -240,20 +264,7 @@ class FrameStore:
         Returns the bytes enqueued (an upper bound: whole stripes of the rect)."""
         if self._copier is None:
             self._copier = SparseFrameCopier(self.width, self.height)
-        c = self._copier
-        key = ("stripes", k, tuple(stripes))
-        r = cover_rect(c._content.get(key), content, self.width, self.height)
-        c._content[key] = content
-        if r is None:
-            return 0
-        x0, y0, x1, y1 = r
-        rows, mod, rem = stripes
-        self._native.call("rt_copy_stripes", self._base + k * self.frame_bytes, src_ptr, 4 * self.width, 4 * x0, 4 * (x1 - x0 + 1), y0, y1,
-                          rows, mod, rem, stream)
-        n = 4 * (x1 - x0 + 1) * sum(min(y1, (s + 1) * rows - 1) - max(y0, s * rows) + 1
-                                    for s in range(y0 // rows, y1 // rows + 1) if s % mod == rem)
-        c.bytes_moved += n
-        return n
+        return self._copier.copy_stripes(k, self._base + k * self.frame_bytes, src_ptr, content, stripes, stream)
 
     def frames(self):
         """(n_frames, H, W) int32 view -- meaningful on rank `dst` after commit()."""

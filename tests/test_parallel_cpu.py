@@ -232,3 +232,128 @@ def test_sparse_push_protocol_world_size_2_gloo():
     finally:
         shm.close()
         shm.unlink()
+
+
+# ---- image-space partition of one frame: stripes -------------------------------------------------------------------
+
+def _fake_native(name, *a):
+    """Host stand-ins for the two copy entry points (semantics as documented in include/rendertoy_b200.h)."""
+    import ctypes
+    if name == "rt_copy_rect":
+        return _fake_copy_rect(name, *a)
+    assert name == "rt_copy_stripes"
+    dst, src, pitch, x_bytes, width_bytes, y0, y1, rows, mod, rem, stream = a
+    assert x_bytes + width_bytes <= pitch and rows >= 1 and 0 <= rem < mod
+    for y in range(y0, y1 + 1):
+        if (y // rows) % mod == rem:
+            ctypes.memmove(dst + y * pitch + x_bytes, src + y * pitch + x_bytes, width_bytes)
+
+
+def test_stripes_are_the_tile_rects():
+    """stripes_of(rank, world) names exactly the rows tile_rects() hands to that rank."""
+    for (w, h, world) in [(3840, 2160, 8), (1920, 1080, 3), (333, 211, 2)]:
+        for r in range(world):
+            rows, mod, rem = parallel.stripes_of(r, world)
+            own = np.zeros(h, bool)
+            for (x0, y0, tw, th) in parallel.tile_rects(w, h, r, world):
+                own[y0:y0 + th] = True
+            assert np.array_equal(own, (np.arange(h) // rows) % mod == rem)
+
+
+def test_stripe_copier_assembles_the_frame(monkeypatch):
+    """Random frames that are clear outside a random content rect, every "rank" pushing only its stripes of the cover rect into
+    two persistent destinations: after all ranks pushed, the destination equals the frame; a rank never writes foreign rows."""
+    from rendertoy_b200 import _native
+    monkeypatch.setattr(_native, "call", _fake_native)
+    rng = np.random.default_rng(11)
+    W, H, world, band = 333, 211, 3, 16
+    copiers = [parallel.SparseFrameCopier(W, H) for _ in range(world)]      # one history per rank, as in the product
+    dests = [np.zeros((H, W), np.uint32) for _ in range(2)]
+    yy = np.arange(H)
+    for it in range(120):
+        src = np.zeros((H, W), np.uint32)
+        if it % 9 == 0:
+            content = (7, 7, 6, 6)
+        elif it % 9 == 1:
+            content = (0, 0, W - 1, H - 1)
+        else:
+            x0, x1 = sorted(rng.integers(0, W, 2)); y0, y1 = sorted(rng.integers(0, H, 2))
+            content = (int(x0), int(y0), int(x1), int(y1))
+        if content[2] >= content[0]:
+            x0, y0, x1, y1 = content
+            src[y0:y1 + 1, x0:x1 + 1] = rng.integers(1, 2 ** 32, (y1 - y0 + 1, x1 - x0 + 1), dtype=np.uint32)
+        d = dests[it % 2]
+        for r in range(world):
+            before = d.copy()
+            copiers[r].copy_stripes(it % 2, d.ctypes.data, src.ctypes.data, content, (band, world, r), None)
+            foreign = (yy // band) % world != r
+            assert np.array_equal(d[foreign], before[foreign]), f"iteration {it}: rank {r} wrote foreign rows"
+        assert np.array_equal(d, src), f"iteration {it}: destination differs from the frame"
+    assert sum(c.bytes_moved for c in copiers) < 0.8 * 120 * W * H * 4
+
+
+def _stripe_worker(rank, world, port, shm_name, w, h, frames, out):
+    """The tile partition's protocol with host stand-ins: rank 0's frame ring is a shared-memory block (CUDA IPC in the product),
+    every rank "renders" the whole synthetic frame locally and pushes only its stripes of the cover rect (rank 0 writes its
+    stripes in place), a gloo all-reduce commits; rank 0 then holds the complete frame."""
+    from multiprocessing import shared_memory
+    from rendertoy_b200 import _native
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    try:
+        _native.call = _fake_native
+        ring = 4
+        store = np.ndarray((ring, h, w), np.uint32, buffer=shm.buf)
+        copier = parallel.SparseFrameCopier(w, h)
+        stripes = parallel.stripes_of(rank, world, band=8)
+        mine = (np.arange(h) // 8) % world == rank
+        flag = torch.zeros(1, dtype=torch.int32)
+        ok = True
+
+        def frame(f):
+            rng = np.random.default_rng(77 + f)
+            img = np.zeros((h, w), np.uint32)
+            if f % 5 == 0:
+                return img, (2, 2, 1, 1)
+            x0, x1 = sorted(rng.integers(0, w, 2)); y0, y1 = sorted(rng.integers(0, h, 2))
+            img[y0:y1 + 1, x0:x1 + 1] = rng.integers(1, 2 ** 32, (y1 - y0 + 1, x1 - x0 + 1), dtype=np.uint32)
+            return img, (int(x0), int(y0), int(x1), int(y1))
+
+        for f in range(frames):
+            img, content = frame(f)
+            slot = f % ring
+            if rank == 0:
+                store[slot][mine] = img[mine]                 # in place: its own stripes, clear pixels included
+            else:
+                copier.copy_stripes(slot, store[slot].ctypes.data, img.ctypes.data, content, stripes, None)
+            dist.all_reduce(flag)                              # commit
+            if rank == 0:
+                ok &= bool(np.array_equal(store[slot], img))
+            dist.barrier()
+        out.put(ok if rank == 0 else copier.bytes_moved < 0.5 * frames * w * h * 4)
+    finally:
+        shm.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_stripe_partition_protocol_world_size_2_gloo():
+    from multiprocessing import shared_memory
+    w, h, frames = 96, 44, 14
+    shm = shared_memory.SharedMemory(create=True, size=4 * w * h * 4)
+    try:
+        np.ndarray((4, h, w), np.uint32, buffer=shm.buf)[:] = 0
+        ctx = mp.get_context("spawn")
+        out = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_stripe_worker, args=(r, 2, port, shm.name, w, h, frames, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(100)
+            assert p.exitcode == 0
+        assert out.get(timeout=5) is True and out.get(timeout=5) is True
+    finally:
+        shm.close()
+        shm.unlink()

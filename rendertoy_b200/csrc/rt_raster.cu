@@ -173,6 +173,12 @@ __device__ __forceinline__ float blend3(float f1, float f2, float f3, float w1, 
 // 2- or 8-warp blocks 49.4 / 49.7; resolve_kernel at 2 or 4 blocks per SM instead of 3: 53.2 / 53.5.
 #define RT_RASTER_MINB (SHADER == RT_SHADER_LESSON08 && !SC ? 7 : 1)
 #endif
+#ifndef RT_COVERAGE_BLOCKS_PER_SM
+// persistent coverage grid: blocks of 128 threads per SM (-D overrides for A/B builds).  Measured on B200 (cfg2, 8 frame streams):
+// 16 blocks per SM 48.7 us per frame, 8 -> 48.4, 4 -> 47.8 (one frame alone +1 us), 2 -> 47.7 (alone +4 us): a smaller grid leaves
+// room for the other frames' kernels while it waits for its few work items.
+#define RT_COVERAGE_BLOCKS_PER_SM 4
+#endif
 #ifndef RT_RESOLVE_MINB
 #define RT_RESOLVE_MINB 3
 #endif
@@ -842,8 +848,8 @@ int launch_draw(const DrawArgs &da, ResolveArgs ra, void *scratch, long long scr
         else raster_kernel<SHADER, false><<<(unsigned)blocks, RW * 32, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
         RT_CUDA(cudaGetLastError());
         if (cap > 0) {
-            if (da.scissor) coverage_kernel<SHADER, true><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
-            else coverage_kernel<SHADER, false><<<rt_sm_count() * 8, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
+            if (da.scissor) coverage_kernel<SHADER, true><<<rt_sm_count() * RT_COVERAGE_BLOCKS_PER_SM, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
+            else coverage_kernel<SHADER, false><<<rt_sm_count() * RT_COVERAGE_BLOCKS_PER_SM, 128, 0, st>>>(da, ctl, items, bigslots, (unsigned)cap);
             RT_CUDA(cudaGetLastError());
         }
     }

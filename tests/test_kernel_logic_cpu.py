@@ -40,3 +40,12 @@ def test_bvh_builders_on_the_cpu_emulator():
     sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
     import check_bvh
     assert check_bvh.main(300, 48, 32, quick=True) == 0
+
+
+@pytest.mark.timeout(600)
+def test_gather_entry_points_on_the_cpu_emulator():
+    """csrc/rt_peer.cu on the host: rt_copy_stripes (the tile partition's 3-D copy) against a row-by-row definition over random
+    rects / stripes / rank counts, rt_push_tiles (tile-sparse push kernel) over cycles of frames, alloc / export / open / copy_rect"""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "cuda_emu"))
+    import check_peer
+    assert check_peer.main(quick=True) == 0

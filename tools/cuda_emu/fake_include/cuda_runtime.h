@@ -61,6 +61,35 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t = nullptr) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+// "device" memory is host memory here; copies are synchronous; IPC handles carry the pointer itself
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, int, cudaStream_t = nullptr)
+{
+    for (size_t r = 0; r < h; ++r) memcpy((char *)d + r * dp, (const char *)s + r * sp, w);
+    return cudaSuccess;
+}
+struct cudaPitchedPtr { void *ptr; size_t pitch, xsize, ysize; };
+struct cudaExtent { size_t width, height, depth; };
+struct cudaPos { size_t x, y, z; };
+struct cudaMemcpy3DParms { void *srcArray; cudaPos srcPos; cudaPitchedPtr srcPtr; void *dstArray; cudaPos dstPos; cudaPitchedPtr dstPtr; cudaExtent extent; int kind; };
+inline cudaPitchedPtr make_cudaPitchedPtr(void *p, size_t pitch, size_t xs, size_t ys) { return cudaPitchedPtr{p, pitch, xs, ys}; }
+inline cudaExtent make_cudaExtent(size_t w, size_t h, size_t d) { return cudaExtent{w, h, d}; }
+inline cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms *p, cudaStream_t = nullptr)
+{   // linear memory on both sides: a slice is ysize rows of pitch bytes
+    for (size_t z = 0; z < p->extent.depth; ++z)
+        for (size_t y = 0; y < p->extent.height; ++y)
+            memcpy((char *)p->dstPtr.ptr + ((z + p->dstPos.z) * p->dstPtr.ysize + y + p->dstPos.y) * p->dstPtr.pitch + p->dstPos.x,
+                   (const char *)p->srcPtr.ptr + ((z + p->srcPos.z) * p->srcPtr.ysize + y + p->srcPos.y) * p->srcPtr.pitch + p->srcPos.x, p->extent.width);
+    return cudaSuccess;
+}
 // linear-memory, point-sampled texture objects only: the "object" is the texel pointer
 template <typename T> inline T tex1Dfetch(cudaTextureObject_t tex, int i) { return reinterpret_cast<const T *>((uintptr_t)tex)[i]; }
 enum { cudaResourceTypeLinear = 2, cudaFilterModePoint = 0, cudaReadModeElementType = 0 };
@@ -140,6 +169,7 @@ inline unsigned atomicMax(unsigned *p, unsigned v)
     return old;
 }
 template <typename T> inline void __stcg(T *p, T v) { *p = v; }
+template <typename T> inline void __stcs(T *p, T v) { *p = v; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 inline unsigned atomicCAS(unsigned *p, unsigned expected, unsigned desired)
 {
@@ -181,6 +211,20 @@ inline void __syncthreads()
     g_emu_block->bar->arrive_and_wait();
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.arrive_and_wait(); }
+// block-wide OR of a predicate (every thread of the block must call it, as on the device)
+inline int __syncthreads_or(int pred)
+{
+    static std::atomic<int> acc[2];            // blocks run one after the other; two phases so a fast thread cannot clear too early
+    static std::atomic<unsigned> phase{0};
+    const unsigned ph = phase.load() & 1u;
+    if (pred) acc[ph].store(1);
+    g_emu_block->bar->arrive_and_wait();
+    const int r = acc[ph].load();
+    g_emu_block->bar->arrive_and_wait();
+    if (threadIdx.x == 0) { acc[ph].store(0); phase.fetch_add(1); }
+    g_emu_block->bar->arrive_and_wait();
+    return r;
+}
 
 // every collective: publish, barrier, read all live lanes, barrier (so nobody overwrites a slot somebody still reads)
 template <typename F> inline auto emu_collective(unsigned long long mine, F combine)

@@ -485,17 +485,25 @@ def bench_raycast(args, rank, world, rows, vb, W=RAY_W, H=RAY_H, lesson=6, frame
             content = rc.render(e2e_targets[j], cam)
             rendered[j].record(st)
             copy_stream.wait_event(rendered[j])
-            reader.copy(i % 2, host[i % 2].data_ptr(), e2e_targets[j].ptr, content if sparse else full_rect, copy_ptr)
+            if sparse == "tiles":     # a kernel stores the non-clear 32x32 tiles straight into the pinned host frame (unified addressing)
+                reader.copy(i % 2, host[i % 2].data_ptr(), e2e_targets[j].ptr, copy_ptr)
+            else:
+                reader.copy(i % 2, host[i % 2].data_ptr(), e2e_targets[j].ptr, content if sparse else full_rect, copy_ptr)
             read_done[j].record(copy_stream)
         e2e_streams.join(copy_stream)
 
     def e2e_measure(n_frames, sparse):
-        reader = parallel.SparseFrameCopier(W, H)
+        tiles = sparse == "tiles"
+        reader = parallel.TileFrameCopier(W, H) if tiles else parallel.SparseFrameCopier(W, H)
         for hbuf in host:
             hbuf.zero_()
         e2e_pass(2 * SUB, 0, reader, sparse)
         barrier_sync(world)
-        reader.bytes_moved = 0
+        if tiles:
+            reader.bytes.zero_()
+            torch.cuda.synchronize()
+        else:
+            reader.bytes_moved = 0
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         e2e_pass(n_frames, 2 * SUB, reader, sparse)
@@ -505,20 +513,25 @@ def bench_raycast(args, rank, world, rows, vb, W=RAY_W, H=RAY_H, lesson=6, frame
         j_last = (n_frames - 1) % SUB
         ok = bool(torch.equal(host[(n_frames - 1) % 2], e2e_targets[j_last].buffer.tensor().view(torch.int32).view(H, W).cpu()))
         assert ok, "read-back: the host frame differs from the device frame"
-        return W * H * n_frames * world / (ms_e * 1e-3) / 1e6, reader.bytes_moved, ok, ms_e
+        return W * H * n_frames * world / (ms_e * 1e-3) / 1e6, (reader.bytes_moved() if tiles else reader.bytes_moved), ok, ms_e
 
     k_e2e = max(2, min(args.steps, 5))
     n_e2e = k_e2e * F
-    e2e_value, e2e_bytes, e2e_ok, e2e_ms = e2e_measure(n_e2e, args.sparse_readback)
+    mode = ("tiles" if args.readback == "tiles" else True) if args.sparse_readback else False
+    e2e_value, e2e_bytes, e2e_ok, e2e_ms = e2e_measure(n_e2e, mode)
     dense_value, dense_bytes, _, dense_ms = e2e_measure(max(SUB * 8, n_e2e // 8), False)
     out["e2e"] = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 192 * F, "d2h_bytes_per_step": e2e_bytes // k_e2e,
                   "frame_bytes_per_step": 4 * W * H * F, "readback_verified": e2e_ok, "steps": k_e2e, "timed_region_ms": e2e_ms,
                   "dense_readback": {"value": dense_value, "unit": "Mrays/s", "d2h_bytes_per_frame": 4 * W * H, "timed_region_ms": dense_ms,
                                      "note": "the same loop reading every frame back whole (33 MB per frame over PCIe)"},
-                  "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> async pitched D2H copy into a pinned, initially cleared "
-                          "host frame" + (" of the pixel rect that can differ from the clear colour (union of the scene's projected bounds of this "
-                          "frame and of the frame the host buffer held before); the host frame is complete and checked against the device frame "
-                          "after the timed region" if args.sparse_readback else " of the whole 33 MB frame") + "; every rank reads back its own frames"}
+                  "readback": "tiles" if mode == "tiles" else ("rect" if mode else "dense"),
+                  "note": "per frame: host matrices -> camera frame -> rt_raycast_primary -> " + (
+                          "rt_push_tiles: a kernel stores the 32x32-pixel tiles that are not the clear colour (or were not in the frame the host "
+                          "buffer held before) straight into the pinned, initially cleared host frame over PCIe (unified addressing)" if mode == "tiles" else
+                          "async pitched D2H copy into a pinned, initially cleared host frame" + (" of the pixel rect that can differ from the clear "
+                          "colour (union of the scene's projected bounds of this frame and of the frame the host buffer held before)" if mode
+                          else " of the whole 33 MB frame")) + "; the host frame is complete and checked against the device frame after the timed "
+                          "region; every rank reads back its own frames"}
     del targets, e2e_targets
     loop.close()
     return out
@@ -614,17 +627,25 @@ def bench_raster(args, rank, world, rows, vb, W=RAS_W, H=RAS_H, frames=None, ful
             lessons.render_frame(ren, raster, vb)
             rendered[j].record(main)
             copy_stream.wait_event(rendered[j])
-            reader.copy(i % 2, host[i % 2].data_ptr(), raster.get_render_target().ptr,
-                        raster.content_rect if args.sparse_readback else full_rect, copy_ptr)
+            if tiles_rb:
+                reader.copy(i % 2, host[i % 2].data_ptr(), raster.get_render_target().ptr, copy_ptr)
+            else:
+                reader.copy(i % 2, host[i % 2].data_ptr(), raster.get_render_target().ptr,
+                            raster.content_rect if args.sparse_readback else full_rect, copy_ptr)
             read_done[j].record(copy_stream)
         main.wait_stream(copy_stream)
 
-    reader = parallel.SparseFrameCopier(W, H)
+    tiles_rb = args.sparse_readback and args.readback == "tiles"
+    reader = parallel.TileFrameCopier(W, H) if tiles_rb else parallel.SparseFrameCopier(W, H)
     e2e_pass(2 * SUB, 0, reader)
     barrier_sync(world)
     k_e2e = max(2, min(args.steps, 5))
     n_e2e = k_e2e * F
-    reader.bytes_moved = 0
+    if tiles_rb:
+        reader.bytes.zero_()
+        torch.cuda.synchronize()
+    else:
+        reader.bytes_moved = 0
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     e2e_pass(n_e2e, 2 * SUB, reader)
@@ -635,11 +656,14 @@ def bench_raster(args, rank, world, rows, vb, W=RAS_W, H=RAS_H, frames=None, ful
     e2e_ok = bool(torch.equal(host[(n_e2e - 1) % 2], last))
     assert e2e_ok, "read-back: the host frame differs from the device frame"
     out["e2e"] = {"value": n_tris * n_e2e * world / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "h2d_bytes_per_step": 192 * F,
-                  "d2h_bytes_per_step": reader.bytes_moved // k_e2e, "frame_bytes_per_step": 4 * W * H * F,
+                  "d2h_bytes_per_step": (reader.bytes_moved() if tiles_rb else reader.bytes_moved) // k_e2e, "frame_bytes_per_step": 4 * W * H * F,
                   "readback_verified": e2e_ok, "steps": k_e2e, "timed_region_ms": e2e_ms,
-                  "note": "per frame: host matrices -> mapped(globals) -> clear, clear, draw_triangles -> async pitched D2H copy into a pinned, "
-                          "initially cleared host frame" + (" of Raster.content_rect (projected bounding box of the drawn mesh, united with the rect "
-                          "of the frame the host buffer held before)" if args.sparse_readback else " of the whole frame")}
+                  "readback": "tiles" if tiles_rb else ("rect" if args.sparse_readback else "dense"),
+                  "note": "per frame: host matrices -> mapped(globals) -> clear, clear, draw_triangles -> " + (
+                          "rt_push_tiles: a kernel stores the non-clear 32x32-pixel tiles (and those that were non-clear in the frame the host buffer "
+                          "held before) straight into the pinned, initially cleared host frame over PCIe" if tiles_rb else
+                          "async pitched D2H copy into a pinned, initially cleared host frame" + (" of Raster.content_rect (projected bounding box of "
+                          "the drawn mesh, united with the rect of the frame the host buffer held before)" if args.sparse_readback else " of the whole frame"))}
     del e2e_rasters, raster0, g0_
     loop.close()
     return out
@@ -1062,6 +1086,9 @@ def main():
     ap.add_argument("--commit-every", type=int, default=4, help="N>1: sub-batches of 8 frames per rank between two commits (4-byte all-reduce)")
     ap.add_argument("--dense-gather", dest="sparse", action="store_false",
                     help="--gather copy: push whole frames instead of the rect that can differ from the clear colour")
+    ap.add_argument("--readback", default="rect", choices=["rect", "tiles"],
+                    help="e2e: rect = copy-engine D2H of the content rect (rt_copy_rect); tiles = rt_push_tiles, a kernel storing the non-clear "
+                         "32x32 tiles into the pinned host frame")
     ap.add_argument("--dense-readback", dest="sparse_readback", action="store_false",
                     help="e2e: read whole frames back instead of the rect that can differ from the clear colour")
     ap.add_argument("--view-refit", type=int, default=None, help="tightening passes over the screen-space nodes (rt_raycast_set_view_refit)")

@@ -162,6 +162,35 @@ class SparseFrameCopier:
         return n
 
 
+class TileFrameCopier:
+    """Moves BGRA8 frames into destinations that persist between frames by 32x32-pixel tiles (rt_push_tiles): a small kernel on
+    the GPU that holds the frame stores only the tiles that hold something other than the clear colour -- or did the last time
+    the same destination was written through this copier -- so that afterwards the destination equals the frame.  The
+    destination may be another GPU's memory (a FrameStore slot: the multi-GPU gather of frame-filling raster frames) or PINNED
+    HOST memory (the read-back of a frame: with unified addressing the kernel's stores cross PCIe directly, and only the
+    covered tiles do).  Destinations must start filled with the clear colour (else pass dirty=True for their first frame)."""
+
+    def __init__(self, width, height):
+        from . import _native
+        self._native, self.width, self.height = _native, width, height
+        self._n = int(_native.lib().rt_push_tiles_state_bytes(width, height))
+        self._state = {}            # destination key -> (uint8 tensor, one byte per tile; clear colour it refers to)
+        self.bytes = torch.zeros(1, dtype=torch.int64, device="cuda")      # bytes stored so far (device counter)
+        torch.cuda.current_stream().synchronize()
+
+    def copy(self, key, dst_ptr, src_ptr, stream, clear_px=0, dirty=False):
+        st = self._state.get(key)
+        if st is None or st[1] != clear_px:
+            t = torch.full((self._n,), 1 if (dirty or st is not None) else 0, dtype=torch.uint8, device="cuda")
+            torch.cuda.current_stream().synchronize()      # filled before a kernel on another stream reads it
+            st = self._state[key] = (t, clear_px)
+        self._native.call("rt_push_tiles", dst_ptr, src_ptr, self.width, self.height, clear_px, st[0].data_ptr(), self.bytes.data_ptr(), stream)
+
+    def bytes_moved(self):
+        """bytes stored so far (synchronises)"""
+        return int(self.bytes.item())
+
+
 class _RawDeviceMemory:
     """Adapter exposing a raw device address to torch through __cuda_array_interface__."""
 
@@ -215,7 +244,7 @@ class FrameStore:
         self.memory = torch.as_tensor(_RawDeviceMemory(self._base, nbytes), device="cuda") if self.ok else None
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda") if self.world > 1 else None
         self._copier = None
-        self._tile_state = None
+        self._tiles = None
         self.tile_bytes = None
         if self.ok and self.world > 1:
             torch.cuda.synchronize()
@@ -242,20 +271,11 @@ class FrameStore:
         into rank dst's memory.  For frames whose bounding rectangle is most of the frame (a frame-filling raster view) this
         moves about half of what push() moves; seven producers doing that is what keeps rank 0's NVLink ingest below its
         ceiling at N = 8.  Do not mix with push() on the same slot.  The bytes stored accumulate in self.tile_bytes (device)."""
-        if self._tile_state is None:
-            n = int(self._native.lib().rt_push_tiles_state_bytes(self.width, self.height))
-            # the store starts zero-filled: exact for clear_px == 0, otherwise every tile has to travel once
-            self._tile_state = torch.full((self.n_frames, n), 0 if clear_px == 0 else 1, dtype=torch.uint8, device="cuda")
-            self.tile_bytes = torch.zeros(1, dtype=torch.int64, device="cuda")
-            self._tile_clear = clear_px
-            torch.cuda.current_stream().synchronize()      # filled before a kernel on another stream reads them
-        if clear_px != self._tile_clear:
-            torch.cuda.synchronize()
-            self._tile_state.fill_(1)
-            self._tile_clear = clear_px
-            torch.cuda.synchronize()
-        self._native.call("rt_push_tiles", self._base + k * self.frame_bytes, src_ptr, self.width, self.height, clear_px,
-                          self._tile_state[k].data_ptr(), self.tile_bytes.data_ptr(), stream)
+        if self._tiles is None:
+            self._tiles = TileFrameCopier(self.width, self.height)
+            self.tile_bytes = self._tiles.bytes
+        # the store starts zero-filled: exact for clear_px == 0, otherwise every tile has to travel once
+        self._tiles.copy(k, self._base + k * self.frame_bytes, src_ptr, stream, clear_px, dirty=clear_px != 0)
 
     def push_stripes(self, k, src_ptr, content, stripes, stream):
         """Image-space partition: copy-engine push of the row stripes (rows, mod, rem) this rank rendered of frame k, from its

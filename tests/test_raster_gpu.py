@@ -313,3 +313,27 @@ def test_frame_store_tile_push(ren):
             assert 0 < moved < lo_frac * 10 * ((w + 31) // 32) * ((h + 31) // 32) * 4096, moved
         finally:
             store.close()
+
+
+def test_tile_readback_into_pinned_host_memory(ren):
+    """parallel.TileFrameCopier with a PINNED HOST destination (the e2e read-back): the rt_push_tiles kernel stores the non-clear
+    tiles of each frame straight into host memory; after every frame the host frame equals the device frame, with fewer bytes
+    crossing PCIe than the frames hold."""
+    import torch
+    from rendertoy_b200 import parallel
+    from rendering._core import stream_ptr
+    w, h = 1920, 1080
+    rows = scenes.dragon(20_000)
+    vb = _upload(ren, rows)
+    raster, g = lessons.build_lesson08(ren, ren.create_presenter(w, h).get_render_target())
+    host = [torch.zeros((h, w), dtype=torch.int32).pin_memory() for _ in range(2)]
+    copier = parallel.TileFrameCopier(w, h)
+    for k in range(8):
+        lessons.set_transforms(ren, g, *scenes.lesson_camera(ren, 8 if k % 3 else 6, 0.6 * k, w, h))
+        lessons.render_frame(ren, raster, vb)
+        copier.copy(k % 2, host[k % 2].data_ptr(), raster.get_render_target().ptr, stream_ptr())
+        torch.cuda.synchronize()
+        frame = raster.get_render_target().buffer.tensor().view(torch.int32).view(h, w).cpu()
+        assert torch.equal(host[k % 2], frame), f"host frame differs from frame {k}"
+        assert frame.any()
+    assert 0 < copier.bytes_moved() < 0.7 * 8 * w * h * 4

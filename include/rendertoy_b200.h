@@ -167,6 +167,10 @@ int rt_raycast_set_view_refit(int passes);
  * world16 may be NULL).  Returns 1, or 0 for a singular view rotation / world matrix or non-finite data. */
 int rt_camera_frame(const float *view16, const float *proj16, const float *world16, float *out12);
 int rt_raycast_screen_bounds(const float *camera, const double *lo, const double *hi, int width, int height, int *rect);
+/* Host only: the same for n boxes (n x 3 doubles each) -- the union of their rectangles; 0 as soon as one box has no bound.  With
+ * the bounds of 64 chunks of the mesh instead of its one box the rectangle (= what a sparse read-back or gather moves, and
+ * what is traced) is a quarter smaller for the dragon orbit. */
+int rt_raycast_screen_bounds_n(const float *camera, const double *lo, const double *hi, int n_boxes, int width, int height, int *rect);
 int rt_raycast_primary(const void *d_nodes, const void *d_tris, int64_t n_triangles, const void *d_pos4,
                        const void *d_nrm4, const int32_t *d_indices, const float *camera, int width, int height,
                        int x0, int y0, int w, int h, int shader, uint64_t tex_handle, void *d_hits, void *d_bgra,
@@ -189,6 +193,7 @@ int rt_dsl_unload(uint64_t module);
  * 0 when the box reaches the near plane (triangles get clipped) or the data is not finite.  A frame is the clear colour
  * outside the union of its draws' rects: only that part has to be read back (rt_copy_rect). */
 int rt_raster_screen_bounds(const float *globals48, const double *lo, const double *hi, int width, int height, int *rect);
+int rt_raster_screen_bounds_n(const float *globals48, const double *lo, const double *hi, int n_boxes, int width, int height, int *rect);
 
 /* ---- OBJ loading  (rendering/_loaders.py:7-33: pywavefront.Wavefront(path, collect_faces=True), then per mesh the first
  * material's interleaved, face-corner-expanded vertices) -- host code, no device work -----------------------------------

@@ -29,6 +29,8 @@ SIGNATURES = {
     "rt_raster_scratch_bytes": (_I64, [_I32, _I64, _I32, _I32]),
     "rt_raster_draw_triangles": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _FP, _U64, _I32, _I32, _VP, _VP, _I64, _VP, _FP, _I32, _U32, C.POINTER(C.c_int), _VP]),
     "rt_raster_screen_bounds": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, C.POINTER(C.c_int)]),
+    "rt_raster_screen_bounds_n": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, _I32, C.POINTER(C.c_int)]),
+    "rt_raycast_screen_bounds_n": (C.c_int, [_FP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32, _I32, _I32, C.POINTER(C.c_int)]),
     "rt_bvh_node_bytes": (_I64, [_I64]),
     "rt_bvh_tri_bytes": (_I64, [_I64]),
     "rt_bvh_scratch_bytes": (_I64, [_I64]),

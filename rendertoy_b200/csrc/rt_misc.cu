@@ -95,6 +95,24 @@ int rt_raster_screen_bounds(const float *globals48, const double *lo, const doub
     return 1;
 }
 
+// The same for n boxes (lo / hi: n x 3 doubles): the union of their rectangles.  A mesh's own bounding box projects to a
+// rectangle a quarter larger than the union of the rectangles of 64 chunks of it (dragon orbit: 0.228 -> 0.175 of the 4K frame
+// for the lesson06 camera, 0.748 -> 0.594 for lesson08), and that rectangle is what every sparse read-back and gather moves.
+// Returns 1 (x1 < x0: nothing on screen), or 0 as soon as one box has no bound.
+int rt_raster_screen_bounds_n(const float *globals48, const double *lo, const double *hi, int n_boxes, int width, int height, int *rect)
+{
+    if (!rect || n_boxes < 1) return 0;
+    int u[4] = {width, height, -1, -1}, r[4];
+    for (int i = 0; i < n_boxes; ++i) {
+        if (!rt_raster_screen_bounds(globals48, lo + 3 * i, hi + 3 * i, width, height, r)) return 0;
+        if (r[2] < r[0] || r[3] < r[1]) continue;
+        u[0] = r[0] < u[0] ? r[0] : u[0]; u[1] = r[1] < u[1] ? r[1] : u[1];
+        u[2] = r[2] > u[2] ? r[2] : u[2]; u[3] = r[3] > u[3] ? r[3] : u[3];
+    }
+    for (int k = 0; k < 4; ++k) rect[k] = u[k];
+    return 1;
+}
+
 int rt_mesh_upload_soa(const void *d_mesh_vertices, int64_t n_vertices, void *d_pos4, void *d_nrm4, void *stream)
 {
     RT_REQUIRE(n_vertices >= 0, "vertex count");

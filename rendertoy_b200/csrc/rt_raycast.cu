@@ -751,6 +751,23 @@ int rt_raycast_screen_bounds(const float *camera, const double *lo, const double
     return 1;
 }
 
+// The same for n boxes (lo / hi: n x 3 doubles, e.g. the bounds of 64 chunks of the Morton-sorted leaves): the union of their
+// rectangles, a quarter smaller than the rectangle of the scene's own box for the dragon orbit.  Returns 1 (x1 < x0: nothing
+// on screen), or 0 as soon as one box has no usable bound.
+int rt_raycast_screen_bounds_n(const float *camera, const double *lo, const double *hi, int n_boxes, int width, int height, int *rect)
+{
+    if (!rect || n_boxes < 1) return 0;
+    int u[4] = {width, height, -1, -1}, r[4];
+    for (int i = 0; i < n_boxes; ++i) {
+        if (!rt_raycast_screen_bounds(camera, lo + 3 * i, hi + 3 * i, width, height, r)) return 0;
+        if (r[2] < r[0] || r[3] < r[1]) continue;
+        u[0] = r[0] < u[0] ? r[0] : u[0]; u[1] = r[1] < u[1] ? r[1] : u[1];
+        u[2] = r[2] > u[2] ? r[2] : u[2]; u[3] = r[3] > u[3] ? r[3] : u[3];
+    }
+    for (int k = 0; k < 4; ++k) rect[k] = u[k];
+    return 1;
+}
+
 // Number of tightening iterations (inside one launch of view_refit_kernel) rt_raycast_primary runs after the projection, 0..64.
 // Process-wide.
 int rt_raycast_set_view_refit(int passes)

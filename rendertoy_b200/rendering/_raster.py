@@ -264,8 +264,8 @@ class Raster:
     @property
     def content_rect(self):
         """Inclusive pixel rect (x0, y0, x1, y1) outside of which the render target holds the colour of the last
-        clear(render_target): the union, over the draws since that clear, of the screen rectangle of each mesh's bounding
-        box under the draw's World/View/Proj (rt_raster_screen_bounds).  The whole frame when that is not known: user
+        clear(render_target): the union, over the draws since that clear, of the screen rectangles of the bounding boxes
+        of 64 chunks of each mesh under the draw's World/View/Proj (rt_raster_screen_bounds_n).  The whole frame when that is not known: user
         vertex shaders, a mesh reaching the near plane, a vertex buffer modified since it was drawn, no clear yet.
         (x1 < x0: nothing was drawn on screen.)  Not part of the reference API; it is what lets a frame be read back or
         gathered sparsely (parallel.SparseFrameCopier).  The first query for a mesh version reads its bounds back (a sync)."""
@@ -280,8 +280,8 @@ class Raster:
         for vb, version, gl in self._draws:
             if vb.version != version:
                 return full
-            lo, hi = _core.mesh_bounds(vb)
-            if not _native.lib().rt_raster_screen_bounds(gl, lo, hi, W, H, r):
+            lo, hi, k = _core.mesh_chunk_bounds(vb)
+            if not _native.lib().rt_raster_screen_bounds_n(gl, lo, hi, k, W, H, r):
                 return full
             if r[2] >= r[0] and r[3] >= r[1]:
                 x0, y0, x1, y1 = min(x0, r[0]), min(y0, r[1]), max(x1, r[2]), max(y1, r[3])

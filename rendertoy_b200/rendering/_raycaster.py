@@ -30,6 +30,8 @@ _MAT16 = ctypes.c_float * 16
 VIEW_NODES_MAX_TRIANGLES = 1 << 18
 # default builder: clustering pays where the traversal is the bound (the screen-space packet path)
 PLOC_MAX_TRIANGLES = 1 << 18
+# render(): the scene's screen-space bound is the union of the projected bounds of this many chunks of the sorted leaves
+SCREEN_CHUNKS = 64
 
 
 @kernel_struct
@@ -149,6 +151,26 @@ class Raycaster:
         _native.call("rt_bvh_build", self.pos4.data_ptr(), self._idx_ptr(), n, self.nodes.data_ptr(), self.tris.data_ptr(),
                      scratch.data_ptr(), _native.BVH_PLOC if self.builder == "ploc" else _native.BVH_LBVH, stream_ptr())
         self._build_scratch = scratch  # kept until the stream has consumed it
+        # Bounds of SCREEN_CHUNKS chunks of the leaves in builder (Morton) order, on the host (one more sync at build time): the
+        # union of their projected rectangles is what render() culls with and returns as the frame's content rect -- a quarter
+        # smaller than the rectangle of the scene's one box for the dragon orbit (0.228 -> 0.175 of the 4K frame).
+        leaves = self.tris.view(torch.float32).view(-1, 12)[:n]
+        v0, e1, e2 = leaves[:, 0:3], leaves[:, 4:7], leaves[:, 8:11]
+        tri_lo = torch.minimum(v0, torch.minimum(v0 + e1, v0 + e2))
+        tri_hi = torch.maximum(v0, torch.maximum(v0 + e1, v0 + e2))
+        k = min(SCREEN_CHUNKS, n)
+        m = -(-n // k)
+        pad = k * m - n
+        if pad:
+            tri_lo = torch.cat([tri_lo, tri_lo[-1:].expand(pad, 3)])
+            tri_hi = torch.cat([tri_hi, tri_hi[-1:].expand(pad, 3)])
+        clo = tri_lo.view(k, m, 3).amin(1).double().cpu().numpy()
+        chi = tri_hi.view(k, m, 3).amax(1).double().cpu().numpy()
+        if not (np.isfinite(clo).all() and np.isfinite(chi).all()):      # non-finite data: the one scene box (no bound either, then)
+            clo, chi = self.scene_lo[None], self.scene_hi[None]
+        self._n_chunks = int(clo.shape[0])
+        self._chunk_lo = (ctypes.c_double * (3 * self._n_chunks))(*clo.reshape(-1).tolist())
+        self._chunk_hi = (ctypes.c_double * (3 * self._n_chunks))(*chi.reshape(-1).tolist())
         self._view_nodes = {}          # stream -> per-frame screen-space nodes of render() (scratch, allocated on first use)
 
     def _idx_ptr(self):
@@ -191,7 +213,7 @@ class Raycaster:
         numpy cost ~50 us of a ~120 us frame."""
         cam = camera if isinstance(camera, _CAM12) else _native.float_array_from_bytes(np.ascontiguousarray(camera, np.float32).reshape(12).view(np.uint8), 12)
         rect = (ctypes.c_int * 4)()
-        if not _native.lib().rt_raycast_screen_bounds(cam, self._lo3, self._hi3, W, H, rect):
+        if not _native.lib().rt_raycast_screen_bounds_n(cam, self._chunk_lo, self._chunk_hi, self._n_chunks, W, H, rect):
             return None
         return rect[0], rect[1], rect[2], rect[3]
 
@@ -232,7 +254,7 @@ class Raycaster:
         content = (x0, y0, x0 + w - 1, y0 + h - 1)
         if cull:
             r = (ctypes.c_int * 4)()
-            if _native.lib().rt_raycast_screen_bounds(cam_c, self._lo3, self._hi3, W, H, r):
+            if _native.lib().rt_raycast_screen_bounds_n(cam_c, self._chunk_lo, self._chunk_hi, self._n_chunks, W, H, r):
                 rect_c = r
                 content = (max(x0, r[0]), max(y0, r[1]), min(x0 + w - 1, r[2]), min(y0 + h - 1, r[3]))
         fast_slab = int(max(abs(cam_c[0]), abs(cam_c[1]), abs(cam_c[2])) <= 16.0 * self.scene_extent)

@@ -375,6 +375,25 @@ def test_raster_screen_bounds_native(ren):
     g = np.concatenate([m.ravel() for m in (hm.rotate(4.5, (0, 1, 0)), hm.look_at((0.12, 0.32, 0.3), (0, 0, 0), (0, 1, 0)),
                                             hm.perspective(aspect_ratio=16 / 9))]).astype(np.float32)
     assert L.rt_raster_screen_bounds(g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), clo, chi, 640, 360, (ctypes.c_int * 4)()) == 0
+    # n boxes (Raster.content_rect: 64 chunks of the mesh): the union of the single rectangles; no bound if one box has none
+    rng = np.random.default_rng(8)
+    centres = rng.uniform(-0.4, 0.4, (9, 3))
+    blo, bhi = centres - rng.uniform(0.01, 0.08, (9, 3)), centres + rng.uniform(0.01, 0.08, (9, 3))
+    nlo, nhi = (ctypes.c_double * 27)(*blo.ravel()), (ctypes.c_double * 27)(*bhi.ravel())
+    for k in range(12):
+        W, H = 1920, 1080
+        mats = [ren.to_array(np.array(m, dtype=ren.float4x4)).astype(np.float32) for m in scenes.lesson_camera(ren, 8 if k % 2 else 6, 0.5 * k, W, H)]
+        gp = np.concatenate([m.ravel() for m in mats]).astype(np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        singles = []
+        for i in range(9):
+            r1 = (ctypes.c_int * 4)()
+            assert L.rt_raster_screen_bounds(gp, (ctypes.c_double * 3)(*blo[i]), (ctypes.c_double * 3)(*bhi[i]), W, H, r1) == 1
+            if r1[2] >= r1[0] and r1[3] >= r1[1]:
+                singles.append(tuple(r1))
+        rn = (ctypes.c_int * 4)()
+        assert L.rt_raster_screen_bounds_n(gp, nlo, nhi, 9, W, H, rn) == 1
+        assert tuple(rn) == (min(r_[0] for r_ in singles), min(r_[1] for r_ in singles), max(r_[2] for r_ in singles), max(r_[3] for r_ in singles))
+    assert L.rt_raster_screen_bounds_n(g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), nlo, nhi, 9, 640, 360, (ctypes.c_int * 4)()) == 0
 
 
 def _random_obj(rng):

@@ -129,11 +129,12 @@ def test_screen_bounds_native_matches_numpy(ren):
     rc.scene_lo, rc.scene_hi = np.array([-0.5, -0.31, -0.22]), np.array([0.5, 0.27, 0.24])
     rc.scene_extent = 1.0
     rc._lo3, rc._hi3 = (ctypes.c_double * 3)(*rc.scene_lo), (ctypes.c_double * 3)(*rc.scene_hi)
+    rc._chunk_lo, rc._chunk_hi, rc._n_chunks = rc._lo3, rc._hi3, 1         # one chunk: the scene box itself
 
-    def numpy_bounds(camera, W, H):
+    def numpy_bounds(camera, W, H, lo=None, hi=None):
         cam = np.asarray(camera, np.float64).reshape(4, 3)
         o, basis = cam[0], cam[1:4].T
-        lo, hi = rc.scene_lo, rc.scene_hi
+        lo, hi = (rc.scene_lo, rc.scene_hi) if lo is None else (lo, hi)
         corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
         try:
             abc = np.linalg.solve(basis, (corners - o).T)
@@ -151,6 +152,21 @@ def test_screen_bounds_native_matches_numpy(ren):
             world, view, proj = scenes.lesson_camera(ren, lesson, 0.37 * k, W, H)
             cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
             assert rc.screen_bounds(cam, W, H) == numpy_bounds(cam, W, H)
+    # several chunk boxes (Raycaster: bounds of 64 chunks of the sorted leaves): the union of the single rectangles
+    rng = np.random.default_rng(4)
+    centres = rng.uniform(-0.4, 0.4, (7, 3))
+    clo, chi = centres - rng.uniform(0.01, 0.1, (7, 3)), centres + rng.uniform(0.01, 0.1, (7, 3))
+    rc._chunk_lo, rc._chunk_hi, rc._n_chunks = (ctypes.c_double * 21)(*clo.ravel()), (ctypes.c_double * 21)(*chi.ravel()), 7
+    for k in range(16):
+        W, H = 1920, 1080
+        world, view, proj = scenes.lesson_camera(ren, 8 if k % 2 else 6, 0.41 * k, W, H)
+        cam = camera_frame(np.array(view, dtype=ren.float4x4), np.array(proj, dtype=ren.float4x4), np.array(world, dtype=ren.float4x4))
+        singles = [numpy_bounds(cam, W, H, clo[i], chi[i]) for i in range(7)]
+        assert all(s_ is not None for s_ in singles)
+        vis = [s_ for s_ in singles if s_[2] >= s_[0] and s_[3] >= s_[1]]
+        want = (min(s_[0] for s_ in vis), min(s_[1] for s_ in vis), max(s_[2] for s_ in vis), max(s_[3] for s_ in vis))
+        assert rc.screen_bounds(cam, W, H) == want
+    rc._chunk_lo, rc._chunk_hi, rc._n_chunks = rc._lo3, rc._hi3, 1
     inside = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)           # eye inside the box
     assert rc.screen_bounds(inside, 640, 480) is None
     singular = np.array([0, 0, 3, 1, 0, 0, 1, 0, 0, 0, 0, -1], np.float32)        # U == V

@@ -1,18 +1,21 @@
-// rt_raster.cu -- Raster.draw_triangles for sm_100a (replaces rendering/_raster.py:416-437 and the seven
-// OpenCL kernels it drives).  Two kernels per draw, no host round trip, no fragment stream:
+// rt_raster.cu -- Raster.draw_triangles / draw_points for sm_100a (replaces rendering/_raster.py:416-437 and the seven
+// OpenCL kernels it drives).  One C-ABI call = up to four launches on the caller's stream, no host round trip, no
+// fragment stream:
 //
-//   raster_kernel   one thread per input triangle: vertex shader x3, near clip into <=2 primitives,
-//                   dehomogenize, bbox + edge setup (all bit-identical to the reference arithmetic), one
-//                   64 B/96 B setup record per primitive; then each warp stages its 32 primitives in shared
-//                   memory and spreads their bbox cells evenly over its lanes, each cell doing the
-//                   reference's coverage test and a 64-bit atomicMin of (depth_bits << 32 | primitive id)
-//                   into the key buffer.
-//   resolve_kernel  one thread per pixel: decode the winning key, re-evaluate that primitive at the pixel
-//                   from its record, perspective-correct attributes, fragment shader once, BGRA8 store,
-//                   re-arm the key's low word for the next draw.
+//   fill_u64        a pending clear(depth_buffer) folded into the draw: key = depth_bits << 32 | NO_PRIMITIVE
+//   raster_kernel   one thread per input triangle: vertex shader x3, near clip into <=2 primitives, dehomogenize, bbox +
+//                   edge setup (all bit-identical to the reference arithmetic), one 64 B/96 B record per primitive; then
+//                   each warp stages its primitives in shared memory, finds the exact accepted interval of every bbox
+//                   row, and runs the reference's coverage test + a 64-bit atomicMin of (depth_bits << 32 | primitive
+//                   id) into the key buffer on full warps of candidate cells.  Large primitives go to a work queue.
+//   coverage_kernel persistent grid draining that queue (row-quads of large primitives)
+//   resolve_kernel  four pixels per thread: decode the winning key, re-evaluate that primitive at the pixel from its
+//                   record, perspective-correct attributes, fragment shader once, BGRA8 store (or the folded clear
+//                   colour), re-arm the key's low word for the next draw.
 //
-// Bound: HBM (vertices in, keys/colour out) with an L2-atomic sub-bound; no dense contraction, so no
-// tensor cores.
+// `owner` (scissor rect + row stripes) restricts all of it to the pixels one rank owns (image-space partition).
+// Bound: instruction issue (raster_kernel) and key -> record latency (resolve_kernel); HBM sees vertices in and
+// keys / colour out at ~16 % of its roofline; no dense contraction, so no tensor cores.
 #include "rt_common.cuh"
 
 namespace {

@@ -2,14 +2,17 @@
 // semantics are those of oracle/raycast_oracle.c: float32 Moller-Trumbore without FMA, closest hit = min over
 // (bits(t) << 32 | triangle id)).
 //
-// One kernel, one warp per 8x4-pixel tile (or 32-ray group), scheduled by the hardware (see raycast_kernel for why not a
-// persistent loop); every lane walks the LBVH with its own short stack (local memory, L1-resident), inner nodes are four
-// 128-bit read-only loads that test both children (three in the per-frame screen-space form), leaves are three.  Primary mode generates the ray from the camera
-// frame in-kernel and shades the hit (Lambert / texture) straight into the BGRA8 frame, so per ray only 4 B
-// (+16 B if hits are requested) leave the SM.
+// Primary rays (rt_raycast_primary), three launches per frame on the caller's stream:
+//   project_kernel     every inner node -> its two children's screen rectangles + minimum depth for THIS camera
+//   view_refit_kernel  a few in-place tightening iterations (a child's rectangle := union of its own children's)
+//   raycast_kernel     one warp per 8x4-pixel tile, scheduled by the hardware: the 32 rays of a tile walk the screen-space
+//                      nodes TOGETHER (one shared-memory stack per warp, broadcast 128-bit loads, votes), leaves run the
+//                      exact Moller-Trumbore, the hit is shaded (Lambert / texture) straight into the BGRA8 frame -- per
+//                      ray only 4 B (+16 B if hits are requested) leave the SM.  `stripes` restricts it to a rank's rows.
+// Arbitrary rays (rt_raycast_rays) and scenes above 2^18 triangles walk the 3-D nodes per lane with a local-memory stack.
 //
-// Bound: FP32 pipe + L1/L2 latency (the BVH of a 100k-triangle mesh is ~11 MB, L2-resident); HBM sees only the
-// frame.  No contraction anywhere, so no tensor cores.
+// Bound: instruction issue (0.82 of one instruction per scheduler and cycle with overlapped frames); the BVH of a
+// 100k-triangle mesh is ~11 MB, L2-resident, HBM sees only the frame.  No contraction anywhere, so no tensor cores.
 #include "rt_common.cuh"
 #include "rt_bvh.cuh"
 

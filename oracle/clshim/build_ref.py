@@ -6,7 +6,7 @@ the reference keeps one global OpenCL program per process) and compiles the resu
 for the host CPU.  Outputs: oracle/_ref/clprog_*.{cpp,so} (git-ignored).  Reference sources are read where they
 lie; nothing is copied into the repo.  tests/golden/*.npz are produced by make_golden.py from these programs.
 
-It also byte-compiles the tutorial scripts that drive the two hot paths (tutorials/lesson06, 08, 09) where they lie into
+It also byte-compiles the nine tutorial scripts (tutorials/lesson01 .. lesson09) where they lie into
 oracle/_ref/tutorials/*.pycode (a .pyc under another extension: the gpurun snapshot drops *.pyc) -- the Python counterpart of compiling a C reference into oracle/_ref/*.so: the GPU box has
 no /root/reference, and tests/test_tutorials_gpu.py executes the UNMODIFIED tutorial programs against this package
 (runpy on the .py here, exec of the unmarshalled code object there).  They are git-ignored build outputs like the .so files.
@@ -40,7 +40,9 @@ print("lesson%02d: %d kernels compiled from the reference's program text" % (les
 '''
 
 
-TUTORIALS = ("lesson06_loading_obj", "lesson08_rasterization", "lesson09_texture_mapping")
+TUTORIALS = ("lesson01_math", "lesson02_vectors_and_matrices", "lesson03_drawing_images", "lesson04_mandelbrot_animation",
+             "lesson05_drawing_points", "lesson06_loading_obj", "lesson07_generative_modeling", "lesson08_rasterization",
+             "lesson09_texture_mapping")
 
 
 def compile_tutorials():
@@ -52,7 +54,7 @@ def compile_tutorials():
         if os.path.exists(src):
             py_compile.compile(src, cfile=os.path.join(out, name + ".pycode"), dfile=f"<reference>/tutorials/{name}.py", doraise=True,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-    print("tutorials: byte-compiled", ", ".join(TUTORIALS), "-> oracle/_ref/tutorials/")
+    print("tutorials: byte-compiled", len(TUTORIALS), "scripts -> oracle/_ref/tutorials/")
 
 
 def main():
